@@ -1,0 +1,86 @@
+// C-ABI glue: error text, launch counter, argument validation and mode dispatch.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace cnb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int conv2d_f32(const cnb_conv_params* p, cudaStream_t st);
+int conv2d_tc(const cnb_conv_params* p, cudaStream_t st);
+bool conv2d_tc_supported(const cnb_conv_params* p);
+int groupnorm(const float* x, float* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
+              float eps, int silu, cudaStream_t st);
+int attention_f32(const float* qkv, float* out, int B, int L, int E, int heads, cudaStream_t st);
+
+static int g_has_tc = -1;
+static int query_tc() {
+  if (g_has_tc >= 0) return g_has_tc;
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;   // not cached: a device may appear later
+  }
+  g_has_tc = (prop.major == 10) ? 1 : 0;
+  return g_has_tc;
+}
+
+}  // namespace cnb
+
+using namespace cnb;
+
+extern "C" int cnb_abi_version(void) { return 1; }
+extern "C" const char* cnb_last_error(void) { return g_err; }
+extern "C" long long cnb_launch_count(void) { return g_launches.load(); }
+extern "C" void cnb_reset_launch_count(void) { g_launches.store(0); }
+extern "C" int cnb_has_tcgen05(void) { return query_tc(); }
+
+extern "C" int cnb_conv2d(const cnb_conv_params* p, cnb_stream_t stream) {
+  CNB_REQUIRE(p != nullptr, "conv2d: null params");
+  CNB_REQUIRE(p->in && p->weight && p->out, "conv2d: null tensor pointer");
+  CNB_REQUIRE(p->B > 0 && p->H > 0 && p->W > 0 && p->Cin > 0 && p->Cout > 0 && p->OH > 0 && p->OW > 0,
+              "conv2d: non-positive dimension");
+  CNB_REQUIRE(p->ntaps >= 1 && p->ntaps <= CNB_MAX_TAPS, "conv2d: ntaps=%d", p->ntaps);
+  CNB_REQUIRE(p->ldi >= p->in_coff + p->Cin && p->ldo >= p->out_coff + p->Cout, "conv2d: leading dimension too small");
+  CNB_REQUIRE(!p->residual || p->ldr >= p->res_coff + p->Cout, "conv2d: residual leading dimension too small");
+  CNB_REQUIRE(!p->temb || p->temb_ld >= p->Cout, "conv2d: temb leading dimension too small");
+  CNB_REQUIRE((long long)p->B * p->OH * p->OW < (1ll << 31), "conv2d: M overflows int32");
+  CNB_REQUIRE((p->OH - 1) * p->oy_mul + p->oy_add < p->OHf && (p->OW - 1) * p->ox_mul + p->ox_add < p->OWf,
+              "conv2d: output mapping exceeds the output tensor");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->mode == CNB_MODE_F32) return conv2d_f32(p, st);
+  if (p->mode == CNB_MODE_TF32 || p->mode == CNB_MODE_BF16) {
+    if (conv2d_tc_supported(p)) return conv2d_tc(p, st);
+    return conv2d_f32(p, st);   // tiny-channel layers (Cin % 4 != 0 or Cout < 16) are HBM-bound CUDA-core work
+  }
+  set_error("conv2d: unknown mode %d", p->mode);
+  return CNB_ERR_BAD_ARG;
+}
+
+extern "C" int cnb_groupnorm(const float* x, float* y, const float* gamma, const float* beta, int B, int HW, int C,
+                             int G, float eps, int silu, cnb_stream_t stream) {
+  CNB_REQUIRE(x && y && gamma && beta && B > 0 && HW > 0 && C > 0 && G > 0, "groupnorm: bad args");
+  return groupnorm(x, y, gamma, beta, B, HW, C, G, eps, silu, (cudaStream_t)stream);
+}
+
+extern "C" int cnb_attention(const float* qkv, float* out, int B, int L, int E, int heads, int mode,
+                             cnb_stream_t stream) {
+  CNB_REQUIRE(qkv && out && B > 0 && L > 0 && E > 0, "attention: bad args");
+  (void)mode;   // every mode currently runs the exact fp32 core; softmax is SFU-bound for d <= 64
+  return attention_f32(qkv, out, B, L, E, heads, (cudaStream_t)stream);
+}

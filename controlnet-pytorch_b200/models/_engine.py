@@ -1,0 +1,327 @@
+"""Execution engine shared by the drop-in modules: parameter containers that reproduce the reference's
+state_dict layout and the channels-last kernel schedule that replaces their ATen forward.
+
+The nn.Conv2d / nn.GroupNorm / nn.MultiheadAttention / nn.Linear objects created here are PARAMETER HOLDERS only:
+they are never called.  Every forward goes through ops.* -> libcnb200.so; a CPU tensor raises (no fallback).
+Kernel-side weight copies (tap-major K-major packing, tf32 rounding) are derived caches attached to the
+parameter object and invalidated by (version counter, data_ptr); they never appear in state_dict().
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .. import runtime as rt
+
+
+# ----------------------------------------------------------------------------------------------------------
+# parameter-holder factories (registration order == reference, so seeded default init is identical)
+# ----------------------------------------------------------------------------------------------------------
+def gn_act_conv3(groups, cin, cout):
+    return nn.Sequential(nn.GroupNorm(groups, cin), nn.SiLU(), nn.Conv2d(cin, cout, 3, 1, 1))
+
+
+def act_linear(din, dout):
+    return nn.Sequential(nn.SiLU(), nn.Linear(din, dout))
+
+
+def zero_(module):
+    for prm in module.parameters():
+        prm.detach().zero_()
+    return module
+
+
+# ----------------------------------------------------------------------------------------------------------
+# derived weight cache
+# ----------------------------------------------------------------------------------------------------------
+def _cached(param, key, builder):
+    store = param.__dict__.setdefault("_cnb_pack", {})
+    stamp = (param._version, param.data_ptr())
+    ent = store.get(key)
+    if ent is None or ent[0] != stamp:
+        with torch.no_grad():
+            ent = (stamp, builder())
+        store[key] = ent
+    return ent[1]
+
+
+def _tc_shape(o, i):
+    """mirror of conv2d_tc_supported (csrc/conv_tc.cu): only layers that reach the tensor core get tf32 weights."""
+    return i % 4 == 0 and o % 16 == 0
+
+
+def packed_conv(param, mode):
+    r = mode != rt.MODE_F32 and _tc_shape(param.shape[0], param.shape[1])
+    return _cached(param, ("conv", r), lambda: ops.pack_conv_weight(param, r))
+
+
+def packed_convT(param, mode):
+    r = mode != rt.MODE_F32 and _tc_shape(param.shape[1], param.shape[0])
+    return _cached(param, ("convT", r), lambda: ops.pack_convT_weight(param, r))
+
+
+def raw(param):
+    """fp32 contiguous parameter used in place (bias, GroupNorm affine, small linears)."""
+    rt.require_cuda(param)
+    if param.dtype != torch.float32 or not param.is_contiguous():
+        raise rt.CnbError("parameters must be contiguous fp32 (the reference's state_dict dtype)")
+    return param.detach()
+
+
+_FACTOR = {}
+
+
+def temb_factor(dim, device):
+    key = (dim, str(device))
+    if key not in _FACTOR:
+        half = dim // 2
+        # same expression as get_time_embedding (models/unet_base.py:20-22), evaluated once on the host
+        f = 10000 ** (torch.arange(start=0, end=half, dtype=torch.float32) / half)
+        _FACTOR[key] = f.to(device)
+    return _FACTOR[key]
+
+
+def as_t(t, device):
+    """torch.as_tensor(t).long(), on the device, at least 1-d (get_time_embedding :16-17)."""
+    t = torch.as_tensor(t)
+    if t.dtype != torch.int64:
+        t = t.long()
+    if t.device != device:
+        t = t.to(device)
+    if t.dim() == 0:
+        t = t.unsqueeze(0)
+    return t.contiguous()
+
+
+def sinusoid(t, dim, device):
+    assert dim % 2 == 0, "time embedding dimension must be divisible by 2"
+    return ops.time_embedding(as_t(t, device), temb_factor(dim, device), dim)
+
+
+def t_proj_mlp(seq, emb):
+    """Linear -> SiLU -> Linear (Unet.t_proj, unet_base.py:313-317)."""
+    h = ops.linear_small(emb, raw(seq[0].weight), raw(seq[0].bias), silu_out=True)
+    return ops.linear_small(h, raw(seq[2].weight), raw(seq[2].bias))
+
+
+class Temb:
+    """Per-layer time-embedding rows for one block: either precomputed (one batched launch per U-Net) or
+    computed lazily from a raw t_emb tensor when a block is called on its own."""
+
+    def __init__(self, table=None, offsets=None, raw_temb=None):
+        self.table, self.offsets, self.raw_temb = table, offsets, raw_temb
+
+    def row(self, block, j):
+        if self.table is not None:
+            off = self.offsets[j]
+            return self.table[:, off:], self.table.shape[1], self.table.shape[0] > 1
+        lin = block.t_emb_layers[j][1]
+        r = ops.linear_small(self.raw_temb, raw(lin.weight), raw(lin.bias), silu_in=True)
+        return r, r.shape[1], r.shape[0] > 1
+
+
+def _check_x(x):
+    rt.require_cuda(x)
+    if x.dtype != torch.float32:
+        raise rt.CnbError("activations must be fp32 (the reference path is fp32 end to end)")
+    return x.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# the residual + self-attention stack common to Down / Mid / Up blocks
+# ----------------------------------------------------------------------------------------------------------
+class ResAttnStack(nn.Module):
+    """Holds resnet_conv_first / t_emb_layers / resnet_conv_second / attention_norms / attentions /
+    residual_input_conv exactly as the reference blocks do (unet_base.py:39-89, blocks.py:40-112)."""
+
+    def _build(self, cin, cout, t_emb_dim, n_res, n_attn, groups, heads, cross_attn=False):
+        if cross_attn:
+            raise NotImplementedError("cross-attention branches are dead for every shipped config (SURVEY.md section 2)")
+        self._groups, self._heads, self.t_emb_dim = groups, heads, t_emb_dim
+        self.resnet_conv_first = nn.ModuleList(
+            [gn_act_conv3(groups, cin if i == 0 else cout, cout) for i in range(n_res)])
+        if t_emb_dim is not None:
+            self.t_emb_layers = nn.ModuleList([act_linear(t_emb_dim, cout) for _ in range(n_res)])
+        self.resnet_conv_second = nn.ModuleList([gn_act_conv3(groups, cout, cout) for _ in range(n_res)])
+        if n_attn:
+            self.attention_norms = nn.ModuleList([nn.GroupNorm(groups, cout) for _ in range(n_attn)])
+            self.attentions = nn.ModuleList(
+                [nn.MultiheadAttention(cout, heads, batch_first=True) for _ in range(n_attn)])
+        self.residual_input_conv = nn.ModuleList(
+            [nn.Conv2d(cin if i == 0 else cout, cout, kernel_size=1) for i in range(n_res)])
+
+    # ---- kernels -------------------------------------------------------------------------------------
+    def _resnet(self, j, x, temb, mode):
+        first, second = self.resnet_conv_first[j], self.resnet_conv_second[j]
+        cout = first[2].out_channels
+        h = ops.groupnorm(x, raw(first[0].weight), raw(first[0].bias), self._groups, silu=True)
+        if temb is not None and self.t_emb_dim is not None:
+            trow, tld, tps = temb.row(self, j)
+        else:
+            trow, tld, tps = None, 0, False
+        h = ops.conv(h, packed_conv(first[2].weight, mode), "3x3", cout, bias=raw(first[2].bias),
+                     temb=trow, temb_ld=tld, temb_per_sample=tps, mode=mode)
+        h = ops.groupnorm(h, raw(second[0].weight), raw(second[0].bias), self._groups, silu=True)
+        rc = self.residual_input_conv[j]
+        r = ops.conv(x, packed_conv(rc.weight, mode), "1x1", cout, bias=raw(rc.bias), mode=mode)
+        return ops.conv(h, packed_conv(second[2].weight, mode), "3x3", cout, bias=raw(second[2].bias),
+                        residual=r, mode=mode)
+
+    def _attention(self, j, x, mode):
+        norm, att = self.attention_norms[j], self.attentions[j]
+        E = att.embed_dim
+        a = ops.groupnorm(x, raw(norm.weight), raw(norm.bias), self._groups, silu=False)
+        qkv = ops.conv(a, packed_conv(att.in_proj_weight, mode), "1x1", 3 * E, bias=raw(att.in_proj_bias), mode=mode)
+        o = ops.attention(qkv, att.num_heads, mode=mode)
+        return ops.conv(o, packed_conv(att.out_proj.weight, mode), "1x1", E, bias=raw(att.out_proj.bias),
+                        residual=x, mode=mode)
+
+    def temb_channels(self):
+        return [seq[1].out_features for seq in self.t_emb_layers] if self.t_emb_dim is not None else []
+
+
+def run_down(block, x, temb, mode):
+    for j in range(block.num_layers):
+        x = block._resnet(j, x, temb, mode)
+        if block.attn:
+            x = block._attention(j, x, mode)
+    if block.down_sample:
+        dc = block.down_sample_conv
+        x = ops.conv(x, packed_conv(dc.weight, mode), "4x4s2", dc.out_channels, bias=raw(dc.bias), mode=mode)
+    return x
+
+
+def run_mid(block, x, temb, mode):
+    x = block._resnet(0, x, temb, mode)
+    for j in range(block.num_layers):
+        x = block._attention(j, x, mode)
+        x = block._resnet(j + 1, x, temb, mode)
+    return x
+
+
+def run_up(block, x, skip, temb, mode, cat=None):
+    """ConvTranspose (4 parity phases) or identity into the first half of the concat buffer, skip in the second
+    half (unet_base.py:267-269).  `cat` may arrive with its second half already written by the producer of the
+    skip (ControlNet zero-conv epilogue), which makes torch.cat free."""
+    B, H, W, C = x.shape
+    if block.up_sample:
+        up = block.up_sample_conv
+        cu = up.out_channels
+        OH, OW = 2 * H, 2 * W
+    else:
+        cu, OH, OW = C, H, W
+    if cat is None:
+        if skip is None:
+            cat = ops.empty(B, OH, OW, cu, device=x.device)
+        else:
+            cat = ops.empty(B, OH, OW, cu + skip.shape[3], device=x.device)
+            ops.copy_channels(skip, cat, d_coff=cu)
+    if block.up_sample:
+        wp = packed_convT(up.weight, mode)
+        for ph in range(4):
+            ops.conv(x, wp[ph], None, cu, bias=raw(up.bias), out=cat, out_coff=0, mode=mode, phase=(ph >> 1, ph & 1))
+    else:
+        ops.copy_channels(x, cat, d_coff=0)
+    x = cat
+    for j in range(block.num_layers):
+        x = block._resnet(j, x, temb, mode)
+        x = block._attention(j, x, mode)
+    return x
+
+
+# ----------------------------------------------------------------------------------------------------------
+# U-Net level helpers (used by Unet / ControlNet / students)
+# ----------------------------------------------------------------------------------------------------------
+def unet_blocks(unet, with_ups=True):
+    blocks = list(unet.downs) + list(unet.mids)
+    if with_ups and hasattr(unet, "ups"):
+        blocks += list(unet.ups)
+    return blocks
+
+
+def temb_plan(unet, temb_vec, with_ups=True):
+    """One launch for all t_emb_layers of a U-Net: rows = SiLU(temb) @ Wcat^T + bcat, Wcat = concat over blocks.
+    Returns {block: Temb}."""
+    blocks = unet_blocks(unet, with_ups)
+    key_params = [seq[1].weight for b in blocks for seq in b.t_emb_layers]
+    holder = key_params[0]
+
+    def build():
+        w = torch.cat([raw(seq[1].weight) for b in blocks for seq in b.t_emb_layers], dim=0).contiguous()
+        bias = torch.cat([raw(seq[1].bias) for b in blocks for seq in b.t_emb_layers], dim=0).contiguous()
+        return w, bias
+
+    store = holder.__dict__.setdefault("_cnb_pack", {})
+    stamp = tuple((p._version, p.data_ptr()) for p in key_params) + tuple(
+        (seq[1].bias._version, seq[1].bias.data_ptr()) for b in blocks for seq in b.t_emb_layers)
+    ent = store.get(("tcat", with_ups))
+    if ent is None or ent[0] != stamp:
+        with torch.no_grad():
+            ent = (stamp, build())
+        store[("tcat", with_ups)] = ent
+    wcat, bcat = ent[1]
+    table = ops.linear_small(temb_vec, wcat, bcat, silu_in=True)
+    plan, off = {}, 0
+    for b in blocks:
+        offs = []
+        for c in b.temb_channels():
+            offs.append(off)
+            off += c
+        plan[b] = Temb(table=table, offsets=offs)
+    return plan
+
+
+def unet_time(unet, t, device):
+    return t_proj_mlp(unet.t_proj, sinusoid(t, unet.t_emb_dim, device))
+
+
+def conv_in(unet, x_nhwc, mode, residual=None):
+    ci = unet.conv_in
+    return ops.conv(x_nhwc, packed_conv(ci.weight, mode), "3x3", ci.out_channels, bias=raw(ci.bias),
+                    residual=residual, mode=mode)
+
+
+def conv_out(unet, x, mode):
+    h = ops.groupnorm(x, raw(unet.norm_out.weight), raw(unet.norm_out.bias), unet.norm_out.num_groups, silu=True)
+    co = unet.conv_out
+    return ops.conv(h, packed_conv(co.weight, mode), "3x3", co.out_channels, bias=raw(co.bias), mode=mode)
+
+
+def run_unet_body(unet, h, plan, mode):
+    """downs (saving their inputs as skips) -> mids -> ups -> norm_out/SiLU/conv_out (unet_base.py:355-374)."""
+    skips = []
+    for d in unet.downs:
+        skips.append(h)
+        h = run_down(d, h, plan[d], mode)
+    for m in unet.mids:
+        h = run_mid(m, h, plan[m], mode)
+    for u in unet.ups:
+        h = run_up(u, h, skips.pop(), plan[u], mode)
+    return conv_out(unet, h, mode)
+
+
+def hint_stack_ddpm(seq, hint_nhwc, mode):
+    """3x3 -> SiLU -> 3x3 -> SiLU -> 3x3 -> SiLU -> 1x1 (controlnet.py:69-89); SiLU is fused in the epilogue."""
+    h = hint_nhwc
+    for idx in (0, 2, 4):
+        c = seq[idx]
+        h = ops.conv(h, packed_conv(c.weight, mode), "3x3", c.out_channels, bias=raw(c.bias), act=1, mode=mode)
+    c = seq[6]
+    return ops.conv(h, packed_conv(c.weight, mode), "1x1", c.out_channels, bias=raw(c.bias), mode=mode)
+
+
+class HintCache:
+    """hint_block(hint) depends on neither t nor x (controlnet.py:179): compute once per (hint object, weights).
+    The cache holds a reference to the hint tensor, so its storage cannot be recycled under the cached key."""
+
+    def __init__(self):
+        self.ref, self.key, self.val = None, None, None
+
+    def get(self, hint, params, mode, fn):
+        key = (hint._version, tuple(hint.shape), mode, tuple((p._version, p.data_ptr()) for p in params))
+        if hint is not self.ref or key != self.key:
+            self.val = fn()
+            self.ref, self.key = hint, key
+        return self.val
+
+    def clear(self):
+        self.ref, self.key, self.val = None, None, None

@@ -1,0 +1,140 @@
+"""Sampling drivers for the hot path: the timestep loop of tools/sample_ddpm_controlnet.py:43-51 /
+tools/sample_ldm_controlnet.py:45-50 with the per-step host work removed.
+
+  * one denoising step (sampler prologue -> ControlNet forward -> fused scheduler update -> step counter bump) is
+    captured ONCE into a CUDA graph and replayed for every timestep: t, the scheduler coefficients and the Philox
+    step are read from device memory, so there is no H2D copy, no host sync and no CPU RNG inside the loop;
+  * noise is Philox keyed by the GLOBAL element index, so the result is independent of how the batch is sharded;
+  * data parallel: each rank owns a contiguous slice of the batch, no collective inside the loop, one all_gather of
+    the final samples (NCCL over NVLink) at the end.
+"""
+import torch
+
+from . import ops
+from . import runtime as rt
+
+_XT_STEP = (1 << 40)   # Philox "step" reserved for drawing x_T
+
+
+class DDPMSampler:
+    def __init__(self, model, scheduler, seed=0, use_graph=True):
+        self.model, self.scheduler, self.seed, self.use_graph = model, scheduler, int(seed), use_graph
+        self._graph = None
+        self._key = None
+
+    # ---- x_T -------------------------------------------------------------------------------------------
+    def draw_xT(self, shape, device, elem_offset=0):
+        return ops.philox_normal(shape, device, self.seed, _XT_STEP, elem_offset)
+
+    # ---- eager loop (injected z, parity tests, per-step callbacks) ----------------------------------------
+    @torch.no_grad()
+    def sample_eager(self, x_T, hint, steps=None, zs=None, elem_offset=0, callback=None):
+        sch = self.scheduler
+        steps = sch.num_timesteps if steps is None else steps
+        table = sch.coef_table(x_T.device)
+        xt, x0 = x_T.contiguous(), None
+        t_dev = torch.empty((1,), device=x_T.device, dtype=torch.int64)
+        for k, t in enumerate(reversed(range(steps))):
+            t_dev.fill_(t)
+            eps = self.model(xt, t_dev, hint)
+            z = zs[k].to(xt.device) if (zs is not None and t > 0) else None
+            xt, x0 = ops.sched_step(xt, eps, table[t], z=z, want_x0=True, seed=self.seed, step=k,
+                                    elem_offset=elem_offset)
+            if callback is not None:
+                callback(t, xt, x0)
+        return xt, x0
+
+    # ---- graph-replayed loop ----------------------------------------------------------------------------
+    def _capture(self, x_T, hint, steps, elem_offset):
+        dev = x_T.device
+        sch = self.scheduler
+        self.xt = x_T.clone().contiguous()
+        self.x0 = torch.empty_like(self.xt)
+        self.t_seq = torch.arange(steps - 1, -1, -1, device=dev, dtype=torch.int64)
+        self.step_idx = torch.zeros((1,), device=dev, dtype=torch.int32)
+        self.t_out = torch.zeros((1,), device=dev, dtype=torch.int64)
+        self.coef = torch.zeros((6,), device=dev, dtype=torch.float32)
+        table = sch.coef_table(dev)
+        L = rt.lib()
+
+        def one_step():
+            rt.check(L.cnb_sampler_prologue(self.step_idx.data_ptr(), self.t_seq.data_ptr(), self.t_out.data_ptr(),
+                                            table.data_ptr(), self.coef.data_ptr(), rt.stream()))
+            eps = self.model(self.xt, self.t_out, hint)
+            ops.sched_step(self.xt, eps, self.coef, z=None, seed=self.seed, step_dev=self.step_idx,
+                           elem_offset=elem_offset, out=self.xt, x0_out=self.x0)
+            rt.check(L.cnb_bump_index(self.step_idx.data_ptr(), 1, rt.stream()))
+
+        # warm-up on a side stream: builds weight / hint caches and sets kernel attributes outside the capture
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            one_step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize(dev)
+        c0 = rt.launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            one_step()
+        self.launches_per_step = rt.launch_count() - c0
+        self._graph = g
+
+    @torch.no_grad()
+    def sample(self, x_T, hint, steps=None, elem_offset=0):
+        """Run t = steps-1 .. 0 (SURVEY.md 3.5 semantics) with fused on-device noise; returns (x_{-1 mean}, x0)."""
+        rt.require_cuda(x_T, hint)
+        steps = self.scheduler.num_timesteps if steps is None else steps
+        if not self.use_graph:
+            return self.sample_eager(x_T, hint, steps, None, elem_offset)
+        key = (tuple(x_T.shape), hint.data_ptr(), tuple(hint.shape), steps, elem_offset, rt.get_mode(), str(x_T.device))
+        if self._graph is None or key != self._key:
+            self._capture(x_T, hint, steps, elem_offset)
+            self._key = key
+        self.xt.copy_(x_T)
+        self.step_idx.zero_()
+        for _ in range(steps):
+            self._graph.replay()
+        return self.xt.clone(), self.x0.clone()
+
+    def replay_steps(self, n, reset=True):
+        """bench.py hook: replay the captured step n times (state continues from wherever it is)."""
+        if reset:
+            self.step_idx.zero_()
+        for _ in range(n):
+            self._graph.replay()
+
+
+def shard_bounds(total, world, rank):
+    """Contiguous slice [lo, hi) of the batch owned by `rank` (remainder spread over the first ranks)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+@torch.no_grad()
+def sample_data_parallel(model, scheduler, shape, hint_fn, steps=None, seed=0, group=None, use_graph=True,
+                         gather=True):
+    """One job over all ranks of `group`: rank r draws and denoises samples [lo, hi) and the final samples are
+    all-gathered once.  `hint_fn(lo, hi)` returns this shard's hint tensor on the local device."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B = shape[0]
+    lo, hi = shard_bounds(B, world, rank)
+    per = 1
+    for d in shape[1:]:
+        per *= d
+    dev = torch.device("cuda", torch.cuda.current_device())
+    smp = DDPMSampler(model, scheduler, seed=seed, use_graph=use_graph)
+    x_T = smp.draw_xT((hi - lo,) + tuple(shape[1:]), dev, elem_offset=lo * per)
+    xt, x0 = smp.sample(x_T, hint_fn(lo, hi), steps=steps, elem_offset=lo * per)
+    if not gather or world == 1:
+        return xt
+    sizes = [shard_bounds(B, world, r) for r in range(world)]
+    if all(b - a == sizes[0][1] - sizes[0][0] for a, b in sizes):
+        out = torch.empty((B,) + tuple(shape[1:]), device=dev, dtype=xt.dtype)
+        dist.all_gather_into_tensor(out, xt.contiguous(), group=group)
+        return out
+    parts = [torch.empty((b - a,) + tuple(shape[1:]), device=dev, dtype=xt.dtype) for a, b in sizes]
+    dist.all_gather(parts, xt.contiguous(), group=group)
+    return torch.cat(parts, dim=0)

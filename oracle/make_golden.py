@@ -1,0 +1,153 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference) on CPU.
+
+Run in the build container only (the GPU box has no /root/reference):
+    python oracle/make_golden.py
+Weights are utils/synthetic.det_state_dict fills of the reference modules' own state_dict keys, inputs are
+det_noise / det_hint, so the vectors can be reproduced on any box from (key, shape, seed) alone.  Only the
+OUTPUTS of the reference are stored.  TEST INFRASTRUCTURE ONLY.
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("CNB_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+syn = importlib.import_module("controlnet-pytorch_b200.utils.synthetic")
+sys.path.insert(0, REF)
+
+from models.controlnet import ControlNet as RefControlNet                       # noqa: E402
+from models.controlnet_ldm import ControlNet as RefControlNetLDM                # noqa: E402
+from models.unet_base import Unet as RefUnet                                    # noqa: E402
+from models.consistency_controlnet_distilled import ConsistencyControlNet as RefCons       # noqa: E402
+from models.distribution_matching_controlnet import DistributionMatchingControlNet as RefDM  # noqa: E402
+from scheduler.linear_noise_scheduler import LinearNoiseScheduler as RefSched   # noqa: E402
+import scheduler.linear_noise_scheduler as ref_sched_mod                        # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def fill(model, seed=0):
+    model.load_state_dict(syn.det_state_dict(model.state_dict(), seed))
+    return model.eval()
+
+
+def inputs(name, B, C, S, hint_size=None, p=0.1):
+    x = syn.det_noise(name + ":x", (B, C, S, S))
+    hint = syn.det_hint(B, hint_size or S, p=p)
+    return x, hint
+
+
+class _InjectZ:
+    """Replace torch.randn inside the reference scheduler module so z is the injected tensor
+    (linear_noise_scheduler.py:71 draws it from the CPU default generator)."""
+
+    def __init__(self, zs):
+        self.zs = list(zs)
+
+    def __enter__(self):
+        self._orig = ref_sched_mod.torch.randn
+        outer = self
+
+        def fake(*a, **k):
+            return outer.zs.pop(0)
+        ref_sched_mod.torch.randn = fake
+        return self
+
+    def __exit__(self, *a):
+        ref_sched_mod.torch.randn = self._orig
+
+
+def trajectory(model, sched, x, hint, steps, name):
+    zs = [syn.det_noise(f"{name}:z{k}", tuple(x.shape)) for k in range(steps)]
+    xt = x
+    with _InjectZ(zs[:steps - 1]):
+        for t in reversed(range(steps)):
+            eps = model(xt, torch.as_tensor(t).unsqueeze(0), hint)
+            xt, x0 = sched.sample_prev_timestep(xt, eps, torch.as_tensor(t))
+    return xt, x0
+
+
+@torch.no_grad()
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+
+    # ---- DDPM ControlNet: tiny / mnist / cifar
+    for name, cfg, B, ts in (("tiny", syn.TINY_PARAMS, 2, (999, 37, 0)),
+                             ("mnist", syn.MNIST_PARAMS, 2, (999, 500, 0)),
+                             ("cifar", syn.CIFAR_PARAMS, 1, (500,))):
+        m = fill(RefControlNet(cfg))
+        x, hint = inputs(name, B, cfg["im_channels"], cfg["im_size"])
+        rec = {"x_sum": x.double().sum().numpy(), "hint_sum": hint.double().sum().numpy()}
+        for t in ts:
+            rec[f"eps_{t}"] = m(x, torch.as_tensor(t).unsqueeze(0), hint).numpy()
+        if name != "cifar":
+            sched = RefSched(**syn.MNIST_DIFFUSION)
+            xt, x0 = trajectory(m, sched, x, hint, 3, name)
+            rec["traj3_xt"], rec["traj3_x0"] = xt.numpy(), x0.numpy()
+        # per-sample t of shape (B,) as used by the training / compare tools
+        if name == "tiny":
+            rec["eps_pers"] = m(x, torch.tensor([10, 700]), hint).numpy()
+        np.savez_compressed(os.path.join(OUT, f"controlnet_{name}.npz"), **rec)
+        print("controlnet", name, {k: getattr(v, "shape", None) for k, v in rec.items()})
+
+    # ---- plain U-Net forward (tools/sample_ddpm.py path)
+    m = fill(RefUnet(syn.TINY_PARAMS))
+    x, _ = inputs("unet_tiny", 2, 1, 16)
+    np.savez_compressed(os.path.join(OUT, "unet_tiny.npz"),
+                        eps_123=m(x, torch.as_tensor(123).unsqueeze(0)).numpy())
+
+    # ---- LDM ControlNet, tiny config (hint 64x64 -> latent 8x8)
+    cfg = syn.TINY_LDM_PARAMS
+    m = fill(RefControlNetLDM(4, cfg, down_sample_factor=8))
+    x, hint = inputs("tiny_ldm", 2, 4, 8, hint_size=64, p=0.05)
+    rec = {}
+    for t in (999, 3):
+        rec[f"eps_{t}"] = m(x, torch.as_tensor(t).unsqueeze(0), hint).numpy()
+    sched = RefSched(ldm_scheduler=True, **syn.CELEBHQ_DIFFUSION)
+    xt, x0 = trajectory(m, sched, x, hint, 3, "tiny_ldm")
+    rec["traj3_xt"], rec["traj3_x0"] = xt.numpy(), x0.numpy()
+    np.savez_compressed(os.path.join(OUT, "controlnet_tiny_ldm.npz"), **rec)
+
+    # ---- students
+    for name, cfg, sigma in (("tiny", syn.TINY_PARAMS, 80.0), ("mnist", syn.MNIST_PARAMS, 80.0),
+                             ("cifar", syn.CIFAR_PARAMS, 5.0)):
+        B = 2 if name != "cifar" else 1
+        m = fill(RefCons(cfg))
+        x, hint = inputs("cons_" + name, B, cfg["im_channels"], cfg["im_size"])
+        rec = {"x0_max": m(x, torch.full((B,), sigma), hint).numpy(),
+               "x0_mid": m(x, torch.full((B,), 1.7), hint).numpy(),
+               "x0_min": m(x, torch.full((B,), 0.001), hint).numpy()}
+        np.savez_compressed(os.path.join(OUT, f"consistency_{name}.npz"), **rec)
+        m = fill(RefDM(cfg))
+        x, hint = inputs("dm_" + name, B, cfg["im_channels"], cfg["im_size"])
+        rec = {"x0_999": m(x, torch.full((B,), 999), hint).numpy()}
+        if B == 2:
+            rec["x0_pers"] = m(x, torch.tensor([5, 400]), hint).numpy()
+        np.savez_compressed(os.path.join(OUT, f"dm_{name}.npz"), **rec)
+        print("students", name)
+
+    # ---- scheduler: tables + steps
+    for name, kw in (("ddpm", dict(syn.MNIST_DIFFUSION)),
+                     ("ldm", dict(syn.CELEBHQ_DIFFUSION, ldm_scheduler=True))):
+        s = RefSched(**kw)
+        rec = dict(betas=s.betas.numpy(), alphas=s.alphas.numpy(), alpha_cum_prod=s.alpha_cum_prod.numpy(),
+                   sqrt_alpha_cum_prod=s.sqrt_alpha_cum_prod.numpy(),
+                   sqrt_one_minus_alpha_cum_prod=s.sqrt_one_minus_alpha_cum_prod.numpy())
+        xt = syn.det_noise("sched:xt", (3, 4, 9, 7))
+        eps = syn.det_noise("sched:eps", (3, 4, 9, 7))
+        z = syn.det_noise("sched:z", (3, 4, 9, 7))
+        for t in (999, 500, 1, 0):
+            with _InjectZ([z]):
+                a, b = s.sample_prev_timestep(xt, eps, torch.as_tensor(t))
+            rec[f"prev_{t}"], rec[f"x0_{t}"] = a.numpy(), b.numpy()
+        np.savez_compressed(os.path.join(OUT, f"scheduler_{name}.npz"), **rec)
+    print("done ->", OUT)
+
+
+if __name__ == "__main__":
+    main()

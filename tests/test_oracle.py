@@ -1,0 +1,131 @@
+"""Pins oracle/cn_oracle.py against the reference's own outputs (tests/golden, made by oracle/make_golden.py)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden, inputs, rel_l2, syn, ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import cn_oracle as O  # noqa: E402
+
+TOL = 2e-5   # fp32 CPU vs fp32 CPU through a different composition of the same ATen primitives
+
+
+def _keys_controlnet(cfg, ldm=False, im_channels=None, dsf=8):
+    """Build the key->shape template without the reference: use the drop-in modules' own state_dict."""
+    pkg = importlib.import_module("controlnet-pytorch_b200")
+    if ldm:
+        mod = importlib.import_module("controlnet-pytorch_b200.models.controlnet_ldm")
+        return mod.ControlNet(im_channels, cfg, down_sample_factor=dsf).state_dict()
+    mod = importlib.import_module("controlnet-pytorch_b200.models.controlnet")
+    return mod.ControlNet(cfg).state_dict()
+
+
+@pytest.mark.parametrize("name,cfg,B,ts", [("tiny", syn.TINY_PARAMS, 2, (999, 37, 0)),
+                                           ("mnist", syn.MNIST_PARAMS, 2, (999, 500, 0)),
+                                           ("cifar", syn.CIFAR_PARAMS, 1, (500,))])
+def test_controlnet_ddpm_vs_golden(name, cfg, B, ts):
+    sd = syn.det_state_dict(_keys_controlnet(cfg))
+    x, hint = inputs(name, B, cfg["im_channels"], cfg["im_size"])
+    g = golden(f"controlnet_{name}")
+    assert abs(float(x.double().sum()) - float(g["x_sum"])) < 1e-9
+    with torch.no_grad():
+        for t in ts:
+            eps = O.controlnet_ddpm_forward(sd, cfg, x, torch.as_tensor(t).unsqueeze(0), hint)
+            assert rel_l2(eps, g[f"eps_{t}"]) < TOL
+        if name == "tiny":
+            eps = O.controlnet_ddpm_forward(sd, cfg, x, torch.tensor([10, 700]), hint)
+            assert rel_l2(eps, g["eps_pers"]) < TOL
+        if name != "cifar":
+            sched = O.SchedulerOracle(**syn.MNIST_DIFFUSION)
+            zs = [syn.det_noise(f"{name}:z{k}", tuple(x.shape)) for k in range(3)]
+            xt, x0 = O.ddpm_sample(lambda a, t, h: O.controlnet_ddpm_forward(sd, cfg, a, t, h), sched, x, hint, 3, zs)
+            assert rel_l2(xt, g["traj3_xt"]) < 5 * TOL
+            assert rel_l2(x0, g["traj3_x0"]) < 5 * TOL
+
+
+def test_controlnet_ldm_vs_golden():
+    cfg = syn.TINY_LDM_PARAMS
+    sd = syn.det_state_dict(_keys_controlnet(cfg, ldm=True, im_channels=4))
+    x, hint = inputs("tiny_ldm", 2, 4, 8, hint_size=64, p=0.05)
+    g = golden("controlnet_tiny_ldm")
+    with torch.no_grad():
+        for t in (999, 3):
+            eps = O.controlnet_ldm_forward(sd, cfg, x, torch.as_tensor(t).unsqueeze(0), hint)
+            assert rel_l2(eps, g[f"eps_{t}"]) < TOL
+        sched = O.SchedulerOracle(ldm_scheduler=True, **syn.CELEBHQ_DIFFUSION)
+        zs = [syn.det_noise(f"tiny_ldm:z{k}", tuple(x.shape)) for k in range(3)]
+        xt, x0 = O.ddpm_sample(lambda a, t, h: O.controlnet_ldm_forward(sd, cfg, a, t, h), sched, x, hint, 3, zs)
+        assert rel_l2(xt, g["traj3_xt"]) < 5 * TOL
+
+
+def test_unet_vs_golden():
+    mod = importlib.import_module("controlnet-pytorch_b200.models.unet_base")
+    sd = syn.det_state_dict(mod.Unet(syn.TINY_PARAMS).state_dict())
+    x, _ = inputs("unet_tiny", 2, 1, 16)
+    with torch.no_grad():
+        eps = O.unet_forward(sd, "", O.base_arch(syn.TINY_PARAMS), x, torch.as_tensor(123).unsqueeze(0))
+    assert rel_l2(eps, golden("unet_tiny")["eps_123"]) < TOL
+
+
+@pytest.mark.parametrize("name,cfg,sigma", [("tiny", syn.TINY_PARAMS, 80.0), ("mnist", syn.MNIST_PARAMS, 80.0),
+                                            ("cifar", syn.CIFAR_PARAMS, 5.0)])
+def test_students_vs_golden(name, cfg, sigma):
+    B = 2 if name != "cifar" else 1
+    cmod = importlib.import_module("controlnet-pytorch_b200.models.consistency_controlnet_distilled")
+    dmod = importlib.import_module("controlnet-pytorch_b200.models.distribution_matching_controlnet")
+    with torch.no_grad():
+        sd = syn.det_state_dict(cmod.ConsistencyControlNet(cfg).state_dict())
+        x, hint = inputs("cons_" + name, B, cfg["im_channels"], cfg["im_size"])
+        g = golden(f"consistency_{name}")
+        assert rel_l2(O.consistency_forward(sd, cfg, x, torch.full((B,), sigma), hint), g["x0_max"]) < TOL
+        assert rel_l2(O.consistency_forward(sd, cfg, x, torch.full((B,), 1.7), hint), g["x0_mid"]) < TOL
+        assert torch.equal(O.consistency_forward(sd, cfg, x, torch.full((B,), 0.001), hint),
+                           torch.from_numpy(g["x0_min"]))
+        sd = syn.det_state_dict(dmod.DistributionMatchingControlNet(cfg).state_dict())
+        x, hint = inputs("dm_" + name, B, cfg["im_channels"], cfg["im_size"])
+        g = golden(f"dm_{name}")
+        assert rel_l2(O.dm_forward(sd, cfg, x, torch.full((B,), 999), hint), g["x0_999"]) < TOL
+        if B == 2:
+            assert rel_l2(O.dm_forward(sd, cfg, x, torch.tensor([5, 400]), hint), g["x0_pers"]) < TOL
+
+
+@pytest.mark.parametrize("name,kw", [("ddpm", dict(syn.MNIST_DIFFUSION)),
+                                     ("ldm", dict(syn.CELEBHQ_DIFFUSION, ldm_scheduler=True))])
+def test_scheduler_bit_exact_vs_golden(name, kw):
+    g = golden(f"scheduler_{name}")
+    s = O.SchedulerOracle(**kw)
+    for k in ("betas", "alphas", "alpha_cum_prod", "sqrt_alpha_cum_prod", "sqrt_one_minus_alpha_cum_prod"):
+        assert np.array_equal(getattr(s, k).numpy(), g[k]), k
+    xt = syn.det_noise("sched:xt", (3, 4, 9, 7))
+    eps = syn.det_noise("sched:eps", (3, 4, 9, 7))
+    z = syn.det_noise("sched:z", (3, 4, 9, 7))
+    for t in (999, 500, 1, 0):
+        a, b = s.sample_prev_timestep(xt, eps, t, z)
+        assert np.array_equal(a.numpy(), g[f"prev_{t}"]), t
+        assert np.array_equal(b.numpy(), g[f"x0_{t}"]), t
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference tree only exists in the build container")
+def test_oracle_vs_live_reference_default_init():
+    """Second pin: default torch init (zero-convs exactly zero) straight from the imported reference."""
+    sys.path.insert(0, "/root/reference")
+    try:
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+        from models.controlnet import ControlNet as Ref
+        torch.manual_seed(3)
+        m = Ref(syn.TINY_PARAMS).eval()
+        x, hint = inputs("live", 2, 1, 16)
+        with torch.no_grad():
+            want = m(x, torch.as_tensor(77).unsqueeze(0), hint)
+            got = O.controlnet_ddpm_forward(m.state_dict(), syn.TINY_PARAMS, x, torch.as_tensor(77).unsqueeze(0), hint)
+        assert rel_l2(got, want) < TOL
+    finally:
+        sys.path.remove("/root/reference")
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
