@@ -1,0 +1,216 @@
+"""Per-kernel parity tests (GPU): every C-ABI entry point against a plain PyTorch fp32 reference of the same op
+(computed on the CPU so no TF32 / cuDNN heuristics are involved)."""
+import importlib
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import golden, rel_l2, syn, ROOT
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+@pytest.fixture(scope="module")
+def pk():
+    pkg = importlib.import_module("controlnet-pytorch_b200")
+    ops = importlib.import_module("controlnet-pytorch_b200.ops")
+    rt = importlib.import_module("controlnet-pytorch_b200.runtime")
+    assert torch.cuda.is_available()
+    rt.lib()
+    return ops, rt
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def rnd(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g)
+
+
+CONV_CASES = [
+    # kind, B, Cin, Cout, H, W
+    ("3x3", 2, 32, 64, 28, 28), ("3x3", 3, 16, 16, 7, 7), ("3x3", 2, 1, 32, 28, 28), ("3x3", 2, 3, 64, 9, 11),
+    ("3x3", 2, 16, 1, 28, 28), ("3x3", 1, 128, 32, 14, 14), ("3x3", 1, 256, 256, 7, 7), ("1x1", 2, 64, 64, 14, 14),
+    ("1x1", 5, 32, 96, 7, 7), ("4x4s2", 2, 64, 64, 28, 28), ("4x4s2", 2, 128, 128, 14, 14), ("3x3s2", 2, 16, 32, 16, 16),
+    ("3x3", 1, 36, 48, 5, 5), ("1x1", 1, 16, 48, 28, 28),
+]
+
+
+def _conv_ref(kind, x, w, b):
+    if kind == "3x3":
+        return F.conv2d(x, w, b, padding=1)
+    if kind == "1x1":
+        return F.conv2d(x, w, b)
+    if kind == "4x4s2":
+        return F.conv2d(x, w, b, stride=2, padding=1)
+    if kind == "3x3s2":
+        return F.conv2d(x, w, b, stride=2, padding=1)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-6), ("tf32", 2e-3)])
+@pytest.mark.parametrize("kind,B,Cin,Cout,H,W", CONV_CASES)
+def test_conv(pk, kind, B, Cin, Cout, H, W, mode, tol):
+    ops, rt = pk
+    m = {"fp32": rt.MODE_F32, "tf32": rt.MODE_TF32}[mode]
+    k = {"3x3": 3, "1x1": 1, "4x4s2": 4, "3x3s2": 3}[kind]
+    x, w, b = rnd(B, Cin, H, W, seed=1), rnd(Cout, Cin, k, k, seed=2) / math.sqrt(Cin * k * k), rnd(Cout, seed=3)
+    want = _conv_ref(kind, x, w, b)
+    temb = rnd(B, Cout, seed=4)
+    res = rnd(*want.shape, seed=5)
+    want_full = F.silu(want + temb[:, :, None, None] + res)
+    wp = ops.pack_conv_weight(w.cuda(), round_tf32=(m != rt.MODE_F32 and Cin % 4 == 0 and Cout % 16 == 0))
+    got = ops.conv(nhwc(x).cuda(), wp, kind, Cout, bias=b.cuda(), mode=m)
+    assert rel_l2(nchw(got.cpu()), want) < tol
+    got = ops.conv(nhwc(x).cuda(), wp, kind, Cout, bias=b.cuda(), temb=temb.cuda(), temb_ld=Cout,
+                   temb_per_sample=True, residual=nhwc(res).cuda(), act=1, mode=m)
+    assert rel_l2(nchw(got.cpu()), want_full) < tol
+    if m == rt.MODE_TF32:
+        assert rt.lib().cnb_tc_error_flag() == 0
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-6), ("tf32", 2e-3)])
+@pytest.mark.parametrize("B,C,H,W", [(2, 32, 7, 7), (1, 64, 14, 14), (3, 16, 5, 3)])
+def test_conv_transpose_into_concat(pk, B, C, H, W, mode, tol):
+    """4 parity phases written into the first half of a 2C-channel concat buffer (UpBlock, unet_base.py:268-269)."""
+    ops, rt = pk
+    m = {"fp32": rt.MODE_F32, "tf32": rt.MODE_TF32}[mode]
+    x, w, b = rnd(B, C, H, W, seed=1), rnd(C, C, 4, 4, seed=2) / math.sqrt(4 * C), rnd(C, seed=3)
+    skip = rnd(B, C, 2 * H, 2 * W, seed=4)
+    want = torch.cat([F.conv_transpose2d(x, w, b, stride=2, padding=1), skip], dim=1)
+    wp = ops.pack_convT_weight(w.cuda(), round_tf32=(m != rt.MODE_F32 and C % 16 == 0))
+    cat = torch.full((B, 2 * H, 2 * W, 2 * C), float("nan"), device="cuda")
+    ops.copy_channels(nhwc(skip).cuda(), cat, d_coff=C)
+    for ph in range(4):
+        ops.conv(nhwc(x).cuda(), wp[ph], None, C, bias=b.cuda(), out=cat, out_coff=0, mode=m, phase=(ph >> 1, ph & 1))
+    assert rel_l2(nchw(cat.cpu()), want) < tol
+
+
+@pytest.mark.parametrize("B,C,G,H,W", [(2, 16, 8, 28, 28), (3, 64, 8, 14, 14), (2, 256, 8, 7, 7), (2, 384, 32, 8, 8),
+                                       (1, 768, 32, 4, 4), (2, 32, 8, 1, 1), (1, 128, 8, 28, 28), (2, 96, 8, 5, 7)])
+@pytest.mark.parametrize("silu", [False, True])
+def test_groupnorm(pk, B, C, G, H, W, silu):
+    ops, rt = pk
+    x = rnd(B, C, H, W, seed=1) * 2.0 + 0.7
+    g, b = 1 + 0.1 * rnd(C, seed=2), 0.1 * rnd(C, seed=3)
+    want = F.group_norm(x, G, g, b, eps=1e-5)
+    if silu:
+        want = F.silu(want)
+    got = ops.groupnorm(nhwc(x).cuda(), g.cuda(), b.cuda(), G, silu)
+    assert rel_l2(nchw(got.cpu()), want) < 3e-6
+
+
+@pytest.mark.parametrize("B,L,E,heads", [(2, 784, 64, 4), (2, 784, 16, 4), (3, 196, 128, 4), (2, 49, 256, 4),
+                                         (2, 196, 32, 4), (1, 1024, 384, 16), (2, 64, 768, 16), (2, 16, 512, 16),
+                                         (1, 64, 512, 4), (1, 100, 384, 4), (1, 50, 768, 4), (2, 1, 64, 4), (1, 13, 32, 4)])
+def test_attention(pk, B, L, E, heads):
+    ops, rt = pk
+    qkv = rnd(B, L, 3 * E, seed=1)
+    d = E // heads
+    q, k, v = [t.reshape(B, L, heads, d).transpose(1, 2) for t in qkv.split(E, dim=-1)]
+    want = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), -1) @ v).transpose(1, 2).reshape(B, L, E)
+    got = ops.attention(qkv.reshape(B, L, 1, 3 * E).cuda(), heads, mode=rt.MODE_F32)
+    assert rel_l2(got.cpu().reshape(B, L, E), want) < 3e-6
+
+
+def test_time_embedding_and_linear(pk):
+    ops, rt = pk
+    import cn_oracle as O
+    eng = importlib.import_module("controlnet-pytorch_b200.models._engine")
+    for D in (32, 128, 512):
+        t = torch.tensor([0, 1, 37, 500, 999])
+        want = O.time_embedding(t, D)
+        got = eng.sinusoid(t, D, torch.device("cuda"))
+        assert (got.cpu() - want).abs().max() < 2e-6
+    x, w, b = rnd(3, 128, seed=1), rnd(50, 128, seed=2) / 11.0, rnd(50, seed=3)
+    want = F.silu(F.linear(F.silu(x), w, b))
+    got = ops.linear_small(x.cuda(), w.cuda(), b.cuda(), silu_in=True, silu_out=True)
+    assert rel_l2(got.cpu(), want) < 2e-6
+
+
+@pytest.mark.parametrize("name,kw", [("ddpm", dict(syn.MNIST_DIFFUSION)),
+                                     ("ldm", dict(syn.CELEBHQ_DIFFUSION, ldm_scheduler=True))])
+def test_scheduler_bit_exact(pk, name, kw):
+    """fp32 bit parity with the reference's sample_prev_timestep outputs (tests/golden, made by the reference)."""
+    sched_mod = importlib.import_module("controlnet-pytorch_b200.scheduler.linear_noise_scheduler")
+    s = sched_mod.LinearNoiseScheduler(**kw)
+    g = golden(f"scheduler_{name}")
+    for k in ("betas", "alphas", "alpha_cum_prod", "sqrt_alpha_cum_prod", "sqrt_one_minus_alpha_cum_prod"):
+        assert np.array_equal(getattr(s, k).numpy(), g[k])
+    xt = syn.det_noise("sched:xt", (3, 4, 9, 7)).cuda()
+    eps = syn.det_noise("sched:eps", (3, 4, 9, 7)).cuda()
+    z = syn.det_noise("sched:z", (3, 4, 9, 7)).cuda()
+    for t in (999, 500, 1, 0):
+        a, b = s.sample_prev_timestep(xt, eps, torch.as_tensor(t), z=z)
+        assert np.array_equal(a.cpu().numpy(), g[f"prev_{t}"]), t
+        assert np.array_equal(b.cpu().numpy(), g[f"x0_{t}"]), t
+
+
+def test_scheduler_reference_rng_default(pk):
+    """Without z the drop-in draws torch.randn on the CPU generator like linear_noise_scheduler.py:71."""
+    sched_mod = importlib.import_module("controlnet-pytorch_b200.scheduler.linear_noise_scheduler")
+    import cn_oracle as O
+    s = sched_mod.LinearNoiseScheduler(**syn.MNIST_DIFFUSION)
+    so = O.SchedulerOracle(**syn.MNIST_DIFFUSION)
+    xt, eps = rnd(2, 1, 28, 28, seed=1), rnd(2, 1, 28, 28, seed=2)
+    torch.manual_seed(123)
+    a, b = s.sample_prev_timestep(xt.cuda(), eps.cuda(), torch.as_tensor(400))
+    torch.manual_seed(123)
+    z = torch.randn(xt.shape)
+    wa, wb = so.sample_prev_timestep(xt, eps, 400, z)
+    assert torch.equal(a.cpu(), wa) and torch.equal(b.cpu(), wb)
+
+
+def test_philox_properties(pk):
+    ops, rt = pk
+    n = 1 << 20
+    a = ops.philox_normal((n,), "cuda", seed=7, step=3)
+    assert abs(float(a.mean())) < 5e-3 and abs(float(a.std()) - 1.0) < 5e-3
+    # sharding invariance: two half-shards with global offsets == one full draw
+    lo = ops.philox_normal((n // 2,), "cuda", seed=7, step=3, elem_offset=0)
+    hi = ops.philox_normal((n // 2,), "cuda", seed=7, step=3, elem_offset=n // 2)
+    assert torch.equal(torch.cat([lo, hi]), a)
+    odd = ops.philox_normal((1001,), "cuda", seed=7, step=3, elem_offset=3)
+    assert torch.equal(odd, a[3:1004])
+    b = ops.philox_normal((n,), "cuda", seed=7, step=4)
+    assert abs(float((a * b).mean())) < 5e-3
+    # the fused scheduler noise is the same stream
+    coef = torch.tensor([0.5, 0.8, 0.01, 0.99, 0.3, 1.0], device="cuda")
+    xt, eps = torch.zeros(4096, device="cuda"), torch.zeros(4096, device="cuda")
+    prev, _ = ops.sched_step(xt, eps, coef, z=None, seed=7, step=3)
+    assert torch.allclose(prev, 0.3 * a[:4096], rtol=0, atol=1e-7)
+
+
+def test_layout_and_scale(pk):
+    ops, rt = pk
+    x = rnd(3, 5, 6, 7, seed=1)
+    assert torch.equal(ops.nchw_to_nhwc(x.cuda()).cpu(), nhwc(x))
+    assert torch.equal(ops.nhwc_to_nchw(nhwc(x).cuda()).cpu(), x)
+    a, c = rnd(3, seed=2), rnd(3, seed=3)
+    y = rnd(3, 5, 6, 7, seed=4)
+    got = ops.scale_rows(a.cuda(), x.cuda(), c.cuda(), y.cuda())
+    want = a[:, None, None, None] * x + c[:, None, None, None] * y
+    assert torch.equal(got.cpu(), want)
+
+
+def test_no_cpu_fallback(pk):
+    ops, rt = pk
+    with pytest.raises(rt.CnbError):
+        ops.groupnorm(torch.zeros(1, 2, 2, 16), torch.ones(16), torch.zeros(16), 8, True)
+    mod = importlib.import_module("controlnet-pytorch_b200.models.controlnet")
+    m = mod.ControlNet(syn.TINY_PARAMS)
+    with pytest.raises(rt.CnbError):
+        m(torch.zeros(1, 1, 16, 16), torch.tensor([3]), torch.zeros(1, 3, 16, 16))

@@ -1,0 +1,188 @@
+"""Whole-path parity (GPU): the drop-in modules on libcnb200 kernels against
+  (1) tests/golden/*.npz - outputs of the UNMODIFIED reference (made by oracle/make_golden.py), and
+  (2) oracle/cn_oracle.py on freshly seeded inputs,
+in both compute modes.  Tolerances are BASELINE.json's: per-step eps rel-L2 <= 1e-4 in fp32 mode, <= 1e-2 in the
+tensor-core mode.
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden, inputs, rel_l2, syn, ROOT
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+TOL = {"fp32": 1e-4, "tf32": 1e-2}
+TRAJ_TOL = {"fp32": 5e-4, "tf32": 3e-2}
+
+
+def _mod(name):
+    return importlib.import_module("controlnet-pytorch_b200." + name)
+
+
+@pytest.fixture(scope="module")
+def rt():
+    r = _mod("runtime")
+    r.lib()
+    return r
+
+
+def _fill(model, seed=0):
+    model.load_state_dict(syn.det_state_dict(model.state_dict(), seed))
+    return model.cuda().eval()
+
+
+def _modes(rt):
+    return ["fp32", "tf32"] if rt.lib().cnb_has_tcgen05() else ["fp32"]
+
+
+@pytest.mark.parametrize("name,cfg,B,ts", [("tiny", syn.TINY_PARAMS, 2, (999, 37, 0)),
+                                           ("mnist", syn.MNIST_PARAMS, 2, (999, 500, 0)),
+                                           ("cifar", syn.CIFAR_PARAMS, 1, (500,))])
+def test_controlnet_ddpm_vs_reference_golden(rt, name, cfg, B, ts):
+    m = _fill(_mod("models.controlnet").ControlNet(cfg))
+    x, hint = inputs(name, B, cfg["im_channels"], cfg["im_size"])
+    g = golden(f"controlnet_{name}")
+    xc, hc = x.cuda(), hint.cuda()
+    for mode in _modes(rt):
+        rt.set_mode(mode)
+        with torch.no_grad():
+            for t in ts:
+                eps = m(xc, torch.as_tensor(t).unsqueeze(0).cuda(), hc)
+                assert eps.shape == x.shape
+                err = rel_l2(eps.cpu(), g[f"eps_{t}"])
+                assert err < TOL[mode], (mode, t, err)
+            if name == "tiny":
+                eps = m(xc, torch.tensor([10, 700]), hc)       # per-sample t, given on the CPU like the tools do
+                assert rel_l2(eps.cpu(), g["eps_pers"]) < TOL[mode]
+            if name != "cifar":
+                sched = _mod("scheduler.linear_noise_scheduler").LinearNoiseScheduler(**syn.MNIST_DIFFUSION)
+                smp = _mod("sampler").DDPMSampler(m, sched, use_graph=False)
+                zs = [syn.det_noise(f"{name}:z{k}", tuple(x.shape)) for k in range(3)]
+                xt, x0 = smp.sample_eager(xc, hc, steps=3, zs=zs)
+                assert rel_l2(xt.cpu(), g["traj3_xt"]) < TRAJ_TOL[mode]
+                assert rel_l2(x0.cpu(), g["traj3_x0"]) < TRAJ_TOL[mode]
+    assert rt.lib().cnb_tc_error_flag() == 0
+
+
+def test_controlnet_ldm_vs_reference_golden(rt):
+    cfg = syn.TINY_LDM_PARAMS
+    m = _fill(_mod("models.controlnet_ldm").ControlNet(4, cfg, down_sample_factor=8))
+    x, hint = inputs("tiny_ldm", 2, 4, 8, hint_size=64, p=0.05)
+    g = golden("controlnet_tiny_ldm")
+    for mode in _modes(rt):
+        rt.set_mode(mode)
+        with torch.no_grad():
+            for t in (999, 3):
+                eps = m(x.cuda(), torch.as_tensor(t).unsqueeze(0).cuda(), hint.cuda())
+                assert rel_l2(eps.cpu(), g[f"eps_{t}"]) < TOL[mode], (mode, t)
+            sched = _mod("scheduler.linear_noise_scheduler").LinearNoiseScheduler(ldm_scheduler=True,
+                                                                                  **syn.CELEBHQ_DIFFUSION)
+            smp = _mod("sampler").DDPMSampler(m, sched, use_graph=False)
+            zs = [syn.det_noise(f"tiny_ldm:z{k}", tuple(x.shape)) for k in range(3)]
+            xt, x0 = smp.sample_eager(x.cuda(), hint.cuda(), steps=3, zs=zs)
+            assert rel_l2(xt.cpu(), g["traj3_xt"]) < TRAJ_TOL[mode]
+
+
+def test_unet_vs_reference_golden(rt):
+    m = _fill(_mod("models.unet_base").Unet(syn.TINY_PARAMS))
+    x, _ = inputs("unet_tiny", 2, 1, 16)
+    for mode in _modes(rt):
+        rt.set_mode(mode)
+        with torch.no_grad():
+            eps = m(x.cuda(), torch.as_tensor(123).unsqueeze(0))
+        assert rel_l2(eps.cpu(), golden("unet_tiny")["eps_123"]) < TOL[mode]
+
+
+@pytest.mark.parametrize("name,cfg,sigma", [("tiny", syn.TINY_PARAMS, 80.0), ("mnist", syn.MNIST_PARAMS, 80.0),
+                                            ("cifar", syn.CIFAR_PARAMS, 5.0)])
+def test_students_vs_reference_golden(rt, name, cfg, sigma):
+    B = 2 if name != "cifar" else 1
+    cons = _fill(_mod("models.consistency_controlnet_distilled").ConsistencyControlNet(cfg))
+    dm = _fill(_mod("models.distribution_matching_controlnet").DistributionMatchingControlNet(cfg))
+    for mode in _modes(rt):
+        rt.set_mode(mode)
+        with torch.no_grad():
+            x, hint = inputs("cons_" + name, B, cfg["im_channels"], cfg["im_size"])
+            g = golden(f"consistency_{name}")
+            xc, hc = x.cuda(), hint.cuda()
+            assert rel_l2(cons(xc, torch.full((B,), sigma).cuda(), hc).cpu(), g["x0_max"]) < TOL[mode]
+            assert rel_l2(cons(xc, torch.full((B,), 1.7).cuda(), hc).cpu(), g["x0_mid"]) < TOL[mode]
+            out = cons(xc, torch.full((B,), 0.001).cuda(), hc)          # boundary: returns x_t itself
+            assert out is xc or torch.equal(out, xc)
+            x, hint = inputs("dm_" + name, B, cfg["im_channels"], cfg["im_size"])
+            g = golden(f"dm_{name}")
+            assert rel_l2(dm(x.cuda(), torch.full((B,), 999).cuda(), hint.cuda()).cpu(), g["x0_999"]) < TOL[mode]
+            if B == 2:
+                assert rel_l2(dm(x.cuda(), torch.tensor([5, 400]).cuda(), hint.cuda()).cpu(), g["x0_pers"]) < TOL[mode]
+
+
+def test_blocks_callable_standalone_vs_oracle(rt):
+    """The public block classes keep the reference's forward(x, t_emb) signatures (NCHW in / NCHW out)."""
+    import cn_oracle as O
+    ub = _mod("models.unet_base")
+    rt.set_mode("fp32")
+    torch.manual_seed(0)
+    x, temb = torch.randn(2, 16, 8, 8), torch.randn(2, 32)
+    d = _fill(ub.DownBlock(16, 32, 32, down_sample=True, num_layers=2))
+    sd = {k: v.cpu() for k, v in d.state_dict().items()}
+    want = O.down_block(sd, "", x, temb, 2, 8, 4, True, True)
+    assert rel_l2(d(x.cuda(), temb.cuda()).cpu(), want) < 1e-5
+    mid = _fill(ub.MidBlock(16, 32, 32, num_layers=1))
+    sd = {k: v.cpu() for k, v in mid.state_dict().items()}
+    assert rel_l2(mid(x.cuda(), temb.cuda()).cpu(), O.mid_block(sd, "", x, temb, 1, 8, 4)) < 1e-5
+    up = _fill(ub.UpBlock(32, 16, 32, up_sample=True, num_layers=1))
+    sd = {k: v.cpu() for k, v in up.state_dict().items()}
+    skip = torch.randn(2, 16, 16, 16)
+    assert rel_l2(up(x.cuda(), skip.cuda(), temb.cuda()).cpu(), O.up_block(sd, "", x, skip, temb, 1, 8, 4, True)) < 1e-5
+
+
+def test_graph_sampler_matches_eager_and_sharding_invariance(rt):
+    """CUDA-graph replayed loop == eager loop bit for bit (same kernels, same Philox stream), and two half-batch
+    shards with global element offsets reproduce the full-batch result (data-parallel invariance)."""
+    cfg = syn.TINY_PARAMS
+    m = _fill(_mod("models.controlnet").ControlNet(cfg))
+    sched = _mod("scheduler.linear_noise_scheduler").LinearNoiseScheduler(**syn.MNIST_DIFFUSION)
+    S = _mod("sampler")
+    rt.set_mode("fp32")
+    B, per = 4, 16 * 16
+    hint = syn.det_hint(B, 16).cuda()
+    g = S.DDPMSampler(m, sched, seed=11, use_graph=True)
+    e = S.DDPMSampler(m, sched, seed=11, use_graph=False)
+    xT = g.draw_xT((B, 1, 16, 16), "cuda")
+    a, a0 = g.sample(xT, hint, steps=5)
+    b, b0 = e.sample(xT, hint, steps=5)
+    assert torch.equal(a, b) and torch.equal(a0, b0)
+    lo = S.DDPMSampler(m, sched, seed=11, use_graph=False)
+    h0, h1 = hint[:2].contiguous(), hint[2:].contiguous()
+    x_lo = lo.draw_xT((2, 1, 16, 16), "cuda", elem_offset=0)
+    x_hi = lo.draw_xT((2, 1, 16, 16), "cuda", elem_offset=2 * per)
+    assert torch.equal(torch.cat([x_lo, x_hi]), xT)
+    c_lo, _ = lo.sample(x_lo, h0, steps=5, elem_offset=0)
+    c_hi, _ = lo.sample(x_hi, h1, steps=5, elem_offset=2 * per)
+    assert rel_l2(torch.cat([c_lo, c_hi]).cpu(), b.cpu()) < 1e-5
+
+
+def test_hint_cache_and_weight_cache_invalidate(rt):
+    cfg = syn.TINY_PARAMS
+    m = _fill(_mod("models.controlnet").ControlNet(cfg))
+    rt.set_mode("fp32")
+    x, hint = inputs("tiny", 2, 1, 16)
+    xc, hc = x.cuda(), hint.cuda()
+    t = torch.tensor([37]).cuda()
+    with torch.no_grad():
+        e1 = m(xc, t, hc)
+        e2 = m(xc, t, hc)                 # cached hint feature
+        assert torch.equal(e1, e2)
+        m.load_state_dict(syn.det_state_dict(m.state_dict(), seed=5))     # in-place copy bumps version counters
+        e3 = m(xc, t, hc)
+        assert rel_l2(e3.cpu(), e1.cpu()) > 1e-2
+        import cn_oracle as O
+        sd = {k: v.cpu() for k, v in m.state_dict().items()}
+        want = O.controlnet_ddpm_forward(sd, cfg, x, torch.tensor([37]), hint)
+        assert rel_l2(e3.cpu(), want) < 1e-4
