@@ -1,0 +1,390 @@
+"""bench.py - headline benchmark of the ControlNet denoising hot path (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B] [--mode tf32|fp32]
+
+Workload : MNIST DDPM ControlNet (config/mnist.yaml model_params), synthetic random-init weights, x_T ~ N(0,1),
+           Canny-like hints (Bernoulli 0.1 in {0,1}, 3 identical channels), per-GPU batch B (default 1024).
+Step     : ONE denoising timestep over the batch = ControlNet forward (eps) + fused sample_prev_timestep, replayed
+           from a CUDA graph (t, scheduler coefficients and Philox step are read on the device).
+Metric   : samples/s of full 1000-step sampling = (N * B) / (1000 * seconds_per_step).
+Multi-GPU: one process per GPU (torchrun), batch sharded, NO collective inside the loop ("weak": B per GPU fixed).
+The line also carries `e2e` (same metric through the public sampler API with pinned-host inputs and a host read of
+the result inside the timed region), `roofline` (dominant kernel family, timed live with CUDA events), `cpu_baseline`
+(the CPU oracle port on the box's host cores, bounded sample) and `clocks` (nvidia-smi under load).
+`--impl reference` times the reference's CPU algorithm (oracle port, all host threads) on the same config/metric.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+METRIC = "controlnet_ddpm_samples_per_sec"
+UNIT = "samples/s"
+STEPS_PER_SAMPLE = 1000
+FLOP_PER_SAMPLE_STEP = 3.878e9          # BASELINE.md section 2 (MNIST ControlNet, 2*MAC convention)
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=float(p["hbm_gbs"]), tf=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    tf_burst=float(p["bf16_tflops"]), src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf=1400.0, tf_burst=1590.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        rows = [r for (ts, r) in self.rows if t0 <= ts <= t1 + 0.15] or [r for (_, r) in self.rows]
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_problem(batch, device, seed_offset=0):
+    import torch
+    syn = importlib.import_module("controlnet-pytorch_b200.utils.synthetic")
+    cn = importlib.import_module("controlnet-pytorch_b200.models.controlnet")
+    sch = importlib.import_module("controlnet-pytorch_b200.scheduler.linear_noise_scheduler")
+    cfg = syn.MNIST_PARAMS
+    model = cn.ControlNet(cfg)
+    model.load_state_dict(syn.det_state_dict(model.state_dict()))
+    model = model.to(device).eval()
+    sched = sch.LinearNoiseScheduler(**syn.MNIST_DIFFUSION)
+    g = torch.Generator().manual_seed(1234 + seed_offset)
+    hint_host = (torch.rand(batch, 1, 28, 28, generator=g) < 0.1).float().repeat(1, 3, 1, 1).contiguous()
+    return cfg, model, sched, hint_host
+
+
+# ------------------------------------------------------------------------------------------------------------
+# roofline: instrumented eager step, CUDA events around every libcnb200 launch on the launching stream
+# ------------------------------------------------------------------------------------------------------------
+def kernel_breakdown(model, sched, x, hint, n_steps=2):
+    import torch
+    ops = importlib.import_module("controlnet-pytorch_b200.ops")
+    S = importlib.import_module("controlnet-pytorch_b200.sampler")
+    rec = []
+    orig = {k: getattr(ops, k) for k in ("conv", "groupnorm", "attention", "sched_step")}
+
+    def timed(name, meta_fn, fn):
+        def w(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            rec.append((name, meta_fn(out, a, k), e0, e1))
+            return out
+        return w
+
+    def conv_meta(out, a, k):
+        x_, w_, kind, cout = a[0], a[1], a[2], a[3]
+        B, H, W, ldi = x_.shape
+        cin = k.get("cin") or (ldi - k.get("in_coff", 0))
+        ntaps = w_.shape[-2] if w_.dim() == 3 else 4
+        if k.get("phase") is not None:
+            OH, OW = H, W
+        else:
+            OH, OW = ops.out_size(kind, H), ops.out_size(kind, W)
+        fam = "conv_tc" if (cin % 4 == 0 and cout % 16 == 0) else "conv_f32"
+        flops = 2.0 * B * OH * OW * ntaps * cin * cout
+        byts = 4.0 * (B * H * W * cin + B * OH * OW * cout * (2 if k.get("residual") is not None else 1) + w_.numel())
+        return dict(fam=fam, flops=flops, bytes=byts)
+
+    ops.conv = timed("conv", conv_meta, orig["conv"])
+    ops.groupnorm = timed("groupnorm", lambda o, a, k: dict(fam="groupnorm", flops=0.0, bytes=8.0 * a[0].numel()),
+                          orig["groupnorm"])
+    ops.attention = timed("attention", lambda o, a, k: dict(
+        fam="attention", bytes=4.0 * (a[0].numel() + o.numel()),
+        flops=4.0 * a[0].shape[0] * (a[0].shape[1] * a[0].shape[2]) ** 2 * (a[0].shape[3] // 3)), orig["attention"])
+    ops.sched_step = timed("sched_step", lambda o, a, k: dict(fam="sched_step", flops=0.0, bytes=16.0 * a[0].numel()),
+                           orig["sched_step"])
+    try:
+        smp = S.DDPMSampler(model, sched, seed=3, use_graph=False)
+        smp.sample_eager(x, hint, steps=1)          # warm caches
+        rec.clear()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        smp.sample_eager(x, hint, steps=n_steps)
+        t1.record()
+        torch.cuda.synchronize()
+    finally:
+        for k_, v in orig.items():
+            setattr(ops, k_, v)
+    fams = {}
+    for name, meta, e0, e1 in rec:
+        f = fams.setdefault(meta["fam"], dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+        f["ms"] += e0.elapsed_time(e1)
+        f["flops"] += meta["flops"]
+        f["bytes"] += meta["bytes"]
+        f["launches"] += 1
+    for f in fams.values():
+        for k_ in ("ms", "flops", "bytes"):
+            f[k_] /= n_steps
+        f["launches"] //= n_steps
+    return fams, t0.elapsed_time(t1) / n_steps
+
+
+def make_roofline(fams, step_ms):
+    pk = _peaks()
+    total = sum(f["ms"] for f in fams.values()) or 1.0
+    dom = max(fams, key=lambda k_: fams[k_]["ms"])
+    f = fams[dom]
+    sec = f["ms"] * 1e-3
+    kernel_names = {"conv_tc": "conv_igemm_tf32_kernel (tcgen05)", "conv_f32": "conv_igemm_f32_kernel",
+                    "groupnorm": "groupnorm_nhwc_kernel", "attention": "attention kernel", "sched_step": "sched_step_kernel"}
+    if dom in ("conv_tc", "attention"):
+        ach = f["flops"] / sec / 1e12
+        r = {"bound": "tensor", "achieved": round(ach, 2), "peak": pk["tf"], "unit": "TFLOP/s",
+             "frac": round(ach / pk["tf"], 4)}
+    else:
+        ach = f["bytes"] / sec / 1e9
+        r = {"bound": "hbm", "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s", "frac": round(ach / pk["hbm"], 4)}
+    r.update({"traffic": None, "kernel": kernel_names.get(dom, dom), "share_of_step": round(f["ms"] / total, 3),
+              "peak_source": pk["src"] + (" (sustained bf16 dense)" if r["bound"] == "tensor" else " (copy)"),
+              "launches_per_step": f["launches"]})
+    fam_out = {}
+    for k_, v in fams.items():
+        s = v["ms"] * 1e-3
+        fam_out[k_] = {"ms": round(v["ms"], 3), "launches": v["launches"],
+                       "TFLOP/s": round(v["flops"] / s / 1e12, 2) if v["flops"] else None,
+                       "GB/s": round(v["bytes"] / s / 1e9, 1)}
+    return r, fam_out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU legs (oracle port = the reference's algorithm on the reference's own ATen CPU kernels)
+# ------------------------------------------------------------------------------------------------------------
+def cpu_oracle_step_fn(batch):
+    import torch
+    syn = importlib.import_module("controlnet-pytorch_b200.utils.synthetic")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cn_oracle as O
+    cn = importlib.import_module("controlnet-pytorch_b200.models.controlnet")
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = syn.MNIST_PARAMS
+    sd = syn.det_state_dict(cn.ControlNet(cfg).state_dict())
+    so = O.SchedulerOracle(**syn.MNIST_DIFFUSION)
+    g = torch.Generator().manual_seed(99)
+    state = {"x": torch.randn(batch, 1, 28, 28, generator=g), "t": 999}
+    hint = (torch.rand(batch, 1, 28, 28, generator=g) < 0.1).float().repeat(1, 3, 1, 1)
+
+    def step():
+        with torch.no_grad():
+            t = state["t"]
+            eps = O.controlnet_ddpm_forward(sd, cfg, state["x"], torch.tensor([t]), hint)
+            z = torch.randn(state["x"].shape)
+            state["x"], _ = so.sample_prev_timestep(state["x"], eps, t, z)
+            state["t"] = t - 1 if t > 1 else 999
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    batch = args.ref_batch
+    step = cpu_oracle_step_fn(batch)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = batch / (dt * STEPS_PER_SAMPLE)
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": round(val, 5), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "mnist_ddpm_controlnet_1000step", "batch_per_step": batch,
+                       "timesteps_per_sample": STEPS_PER_SAMPLE, "step": "one denoising timestep on the CPU"},
+            "cpu_baseline": {"value": round(val, 5), "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} timesteps x batch {batch} (oracle/cn_oracle.py, torch CPU fp32)"},
+            "e2e": {"value": round(val, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rt = importlib.import_module("controlnet-pytorch_b200.runtime")
+    S = importlib.import_module("controlnet-pytorch_b200.sampler")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rt.lib()
+    rt.set_mode(args.mode)
+    B = args.batch
+    cfg, model, sched, hint_host = build_problem(B, dev, seed_offset=rank)
+    per = 28 * 28
+    smp = S.DDPMSampler(model, sched, seed=5, use_graph=True)
+    hint = hint_host.to(dev)
+    x_T = smp.draw_xT((B, 1, 28, 28), dev, elem_offset=rank * B * per)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: K graph replays of the captured timestep ---------------------------
+    with torch.no_grad():
+        smp._capture(x_T, hint, STEPS_PER_SAMPLE, rank * B * per)
+    smp.replay_steps(max(args.warmup, 3), reset=True)
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    e0.record()
+    smp.replay_steps(args.steps, reset=False)
+    e1.record()
+    barrier()
+    w1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    if rank == 0:
+        clk.stop()
+    value = world * B / (ms_per_step * 1e-3 * STEPS_PER_SAMPLE)
+    launches = smp.launches_per_step * args.steps
+
+    # ---- end to end through the public sampler API with host buffers ----------------------------------
+    xh = torch.randn(B, 1, 28, 28).pin_memory()
+    hh = hint_host.pin_memory()
+    out_h = torch.empty(B, 1, 28, 28).pin_memory()
+    k_e2e = args.steps
+    smp2 = S.DDPMSampler(model, sched, seed=6, use_graph=True)
+    with torch.no_grad():
+        hd = hh.to(dev, non_blocking=True)
+        smp2.sample(xh.to(dev), hd, steps=k_e2e, elem_offset=rank * B * per)       # capture + warm
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        xd = xh.to(dev, non_blocking=True)
+        hd.copy_(hh, non_blocking=True)
+        xt, _ = smp2.sample(xd, hd, steps=k_e2e, elem_offset=rank * B * per)
+        out_h.copy_(xt, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+    ms2 = torch.tensor([max(e0.elapsed_time(e1), (t1 - t0) * 1e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms_per_step = float(ms2.item()) / k_e2e
+    e2e_val = world * B / (e2e_ms_per_step * 1e-3 * STEPS_PER_SAMPLE)
+    e2e = {"value": round(e2e_val, 3), "unit": UNIT,
+           "h2d_bytes_per_step": int((xh.numel() + hh.numel()) * 4 / k_e2e),
+           "d2h_bytes_per_step": int(out_h.numel() * 4 / k_e2e),
+           "note": f"public DDPMSampler.sample(x_T, hint, steps={k_e2e}) per call: pinned-host x_T+hint H2D, {k_e2e} "
+                   f"timesteps, final x D2H, all inside the timed region; normalised to {STEPS_PER_SAMPLE} timesteps/sample"}
+
+    # ---- roofline of the dominant kernel family + CPU baseline (rank 0) ----------------------------------
+    roofline, fam = None, None
+    cpu_baseline = None
+    if rank == 0:
+        with torch.no_grad():
+            fams, eager_ms = kernel_breakdown(model, sched, x_T, hint, n_steps=2)
+        roofline, fam = make_roofline(fams, eager_ms)
+        if world == 1 and not args.no_cpu:
+            nb, ns = args.cpu_batch, args.cpu_steps
+            step = cpu_oracle_step_fn(nb)
+            step()
+            t0 = time.perf_counter()
+            for _ in range(ns):
+                step()
+            dt = (time.perf_counter() - t0) / ns
+            cpu_baseline = {"value": round(nb / (dt * STEPS_PER_SAMPLE), 5), "unit": UNIT,
+                            "cores": torch.get_num_threads(), "kind": "port",
+                            "sample": f"{ns} timesteps x batch {nb} of the same workload (oracle/cn_oracle.py, torch CPU "
+                                      f"fp32, {os.cpu_count()} host CPUs), {dt * 1e3:.0f} ms/timestep"}
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
+                "config": {"workload": "mnist_ddpm_controlnet_1000step", "batch_per_gpu": B, "global_batch": world * B,
+                           "timesteps_per_sample": STEPS_PER_SAMPLE,
+                           "step": "one denoising timestep: ControlNet eps + fused sample_prev_timestep (CUDA graph replay)",
+                           "parallelism": f"dp{world} (batch-sharded, no collective in the loop)",
+                           "l2": "inputs larger than L2: ~%.1f GB of activations per step vs 126 MB L2" % (
+                               B * 2.98e6 * 4 * 2 / 1e9),
+                           "sample_steps_per_sec": round(world * B / (ms_per_step * 1e-3), 1),
+                           "model_tflops": round(world * B * FLOP_PER_SAMPLE_STEP / (ms_per_step * 1e-3) / 1e12, 2)},
+                "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": int(smp.launches_per_step),
+                "roofline": roofline, "kernel_families": fam, "cpu_baseline": cpu_baseline,
+                "clocks": clk.summary(w0, w1)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="per-GPU batch")
+    ap.add_argument("--mode", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--ref-batch", type=int, default=64)
+    ap.add_argument("--cpu-batch", type=int, default=64)
+    ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

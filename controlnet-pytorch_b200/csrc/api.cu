@@ -26,6 +26,8 @@ bool conv2d_tc_supported(const cnb_conv_params* p);
 int groupnorm(const float* x, float* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
               float eps, int silu, cudaStream_t st);
 int attention_f32(const float* qkv, float* out, int B, int L, int E, int heads, cudaStream_t st);
+int attention_tc(const float* qkv, float* out, int B, int L, int E, int heads, cudaStream_t st);
+bool attention_tc_supported(int E, int heads);
 
 static int g_has_tc = -1;
 static int query_tc() {
@@ -81,6 +83,7 @@ extern "C" int cnb_groupnorm(const float* x, float* y, const float* gamma, const
 extern "C" int cnb_attention(const float* qkv, float* out, int B, int L, int E, int heads, int mode,
                              cnb_stream_t stream) {
   CNB_REQUIRE(qkv && out && B > 0 && L > 0 && E > 0, "attention: bad args");
-  (void)mode;   // every mode currently runs the exact fp32 core; softmax is SFU-bound for d <= 64
-  return attention_f32(qkv, out, B, L, E, heads, (cudaStream_t)stream);
+  if (mode != CNB_MODE_F32 && attention_tc_supported(E, heads))
+    return attention_tc(qkv, out, B, L, E, heads, (cudaStream_t)stream);
+  return attention_f32(qkv, out, B, L, E, heads, (cudaStream_t)stream);   // exact fp32 core (and odd head dims)
 }

@@ -78,6 +78,7 @@ class DDPMSampler:
             one_step()
         self.launches_per_step = rt.launch_count() - c0
         self._graph = g
+        self._nsteps, self._pos = steps, 0
 
     @torch.no_grad()
     def sample(self, x_T, hint, steps=None, elem_offset=0):
@@ -91,17 +92,20 @@ class DDPMSampler:
             self._capture(x_T, hint, steps, elem_offset)
             self._key = key
         self.xt.copy_(x_T)
-        self.step_idx.zero_()
-        for _ in range(steps):
-            self._graph.replay()
+        self.replay_steps(steps, reset=True)
         return self.xt.clone(), self.x0.clone()
 
     def replay_steps(self, n, reset=True):
         """bench.py hook: replay the captured step n times (state continues from wherever it is)."""
         if reset:
             self.step_idx.zero_()
+            self._pos = 0
         for _ in range(n):
+            if self._pos >= self._nsteps:      # wrap around the schedule instead of running off the t table
+                self.step_idx.zero_()
+                self._pos = 0
             self._graph.replay()
+            self._pos += 1
 
 
 def shard_bounds(total, world, rank):

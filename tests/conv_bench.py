@@ -1,0 +1,73 @@
+"""Development micro-benchmark (GPU box; not collected by pytest): times individual hot shapes of the MNIST
+ControlNet step at batch 1024 with CUDA events so a kernel change can be judged in one short gpurun call.
+    python tests/conv_bench.py [conv|attn|gn|all] [reps]"""
+import importlib
+import math
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+ops = importlib.import_module("controlnet-pytorch_b200.ops")
+rt = importlib.import_module("controlnet-pytorch_b200.runtime")
+rt.lib()
+what = sys.argv[1] if len(sys.argv) > 1 else "all"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+B = int(os.environ.get("CB_BATCH", "1024"))
+
+
+def timeit(fn):
+    fn()
+    torch.cuda.synchronize()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+if what in ("conv", "all"):
+    shapes = [("3x3", 256, 256, 7), ("3x3", 128, 128, 7), ("3x3", 128, 128, 14), ("3x3", 64, 64, 28),
+              ("3x3", 64, 128, 14), ("3x3", 32, 64, 28), ("3x3", 16, 16, 28), ("3x3", 64, 16, 28),
+              ("1x1", 64, 192, 28), ("1x1", 64, 64, 28), ("1x1", 256, 768, 7), ("1x1", 256, 256, 7),
+              ("4x4s2", 64, 64, 28), ("3x3", 128, 32, 28)]
+    for mode in (rt.MODE_TF32, rt.MODE_F32):
+        for kind, cin, cout, hw in shapes:
+            k = {"3x3": 9, "1x1": 1, "4x4s2": 16}[kind]
+            x = torch.randn(B, hw, hw, cin, device="cuda")
+            w = torch.randn(cout, k, cin, device="cuda") / math.sqrt(k * cin)
+            bias = torch.randn(cout, device="cuda")
+            oh = ops.out_size(kind, hw)
+            out = torch.empty(B, oh, oh, cout, device="cuda")
+            ms = timeit(lambda: ops.conv(x, w, kind, cout, bias=bias, out=out, mode=mode))
+            fl = 2.0 * B * oh * oh * k * cin * cout
+            by = 4.0 * (x.numel() + out.numel() + w.numel())
+            print(f"conv[{rt.mode_name(mode)}] {kind} {cin}->{cout} @{hw}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:8.1f} TFLOP/s  "
+                  f"{by / ms / 1e6:8.1f} GB/s(min-traffic)", flush=True)
+
+if what in ("attn", "all"):
+    for mode in (rt.MODE_TF32, rt.MODE_F32):
+        for L, E, heads in [(784, 64, 4), (784, 16, 4), (196, 128, 4), (196, 32, 4), (49, 256, 4), (49, 128, 4), (49, 64, 4)]:
+            side = int(math.isqrt(L))
+            qkv = torch.randn(B, side, side, 3 * E, device="cuda")
+            ms = timeit(lambda: ops.attention(qkv, heads, mode=mode))
+            fl = 4.0 * B * L * L * E
+            print(f"attn[{rt.mode_name(mode)}] L={L} E={E} d={E // heads}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:8.2f} TFLOP/s  "
+                  f"{B * heads * L * L / ms / 1e6:8.2f} Gscore/s", flush=True)
+
+if what in ("gn", "all"):
+    for C, hw, G in [(64, 28, 8), (32, 28, 8), (16, 28, 8), (128, 14, 8), (256, 7, 8), (128, 7, 8)]:
+        x = torch.randn(B, hw, hw, C, device="cuda")
+        g, b = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+        ms = timeit(lambda: ops.groupnorm(x, g, b, G, True))
+        print(f"gn C={C} @{hw}: {ms * 1e3:8.1f} us  {8.0 * x.numel() / ms / 1e6:8.1f} GB/s", flush=True)
+print("flag", rt.lib().cnb_tc_error_flag())

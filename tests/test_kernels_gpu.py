@@ -116,14 +116,16 @@ def test_groupnorm(pk, B, C, G, H, W, silu):
 @pytest.mark.parametrize("B,L,E,heads", [(2, 784, 64, 4), (2, 784, 16, 4), (3, 196, 128, 4), (2, 49, 256, 4),
                                          (2, 196, 32, 4), (1, 1024, 384, 16), (2, 64, 768, 16), (2, 16, 512, 16),
                                          (1, 64, 512, 4), (1, 100, 384, 4), (1, 50, 768, 4), (2, 1, 64, 4), (1, 13, 32, 4)])
-def test_attention(pk, B, L, E, heads):
+@pytest.mark.parametrize("mode,tol", [("fp32", 3e-6), ("tf32", 2e-3)])
+def test_attention(pk, B, L, E, heads, mode, tol):
     ops, rt = pk
+    m = {"fp32": rt.MODE_F32, "tf32": rt.MODE_TF32}[mode]
     qkv = rnd(B, L, 3 * E, seed=1)
     d = E // heads
     q, k, v = [t.reshape(B, L, heads, d).transpose(1, 2) for t in qkv.split(E, dim=-1)]
     want = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), -1) @ v).transpose(1, 2).reshape(B, L, E)
-    got = ops.attention(qkv.reshape(B, L, 1, 3 * E).cuda(), heads, mode=rt.MODE_F32)
-    assert rel_l2(got.cpu().reshape(B, L, E), want) < 3e-6
+    got = ops.attention(qkv.reshape(B, L, 1, 3 * E).cuda(), heads, mode=m)
+    assert rel_l2(got.cpu().reshape(B, L, E), want) < tol
 
 
 def test_time_embedding_and_linear(pk):
