@@ -23,8 +23,8 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int conv2d_f32(const cnb_conv_params* p, cudaStream_t st);
 int conv2d_tc(const cnb_conv_params* p, cudaStream_t st);
 bool conv2d_tc_supported(const cnb_conv_params* p);
-int groupnorm(const float* x, float* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
-              float eps, int silu, cudaStream_t st);
+int groupnorm(const float* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
+              float eps, int silu, int out_f16, cudaStream_t st);
 int attention_f32(const float* qkv, float* out, int B, int L, int E, int heads, cudaStream_t st);
 int attention_tc(const float* qkv, float* out, int B, int L, int E, int heads, cudaStream_t st);
 bool attention_tc_supported(int E, int heads);
@@ -47,6 +47,7 @@ static int query_tc() {
 using namespace cnb;
 
 extern "C" int cnb_abi_version(void) { return 1; }
+extern "C" int cnb_sizeof_conv_params(void) { return (int)sizeof(cnb_conv_params); }
 extern "C" const char* cnb_last_error(void) { return g_err; }
 extern "C" long long cnb_launch_count(void) { return g_launches.load(); }
 extern "C" void cnb_reset_launch_count(void) { g_launches.store(0); }
@@ -65,19 +66,22 @@ extern "C" int cnb_conv2d(const cnb_conv_params* p, cnb_stream_t stream) {
   CNB_REQUIRE((p->OH - 1) * p->oy_mul + p->oy_add < p->OHf && (p->OW - 1) * p->ox_mul + p->ox_add < p->OWf,
               "conv2d: output mapping exceeds the output tensor");
   cudaStream_t st = (cudaStream_t)stream;
-  if (p->mode == CNB_MODE_F32) return conv2d_f32(p, st);
+  CNB_REQUIRE(p->in_dtype == 0 || p->in_dtype == 1, "conv2d: in_dtype=%d", p->in_dtype);
   if (p->mode == CNB_MODE_TF32 || p->mode == CNB_MODE_BF16) {
     if (conv2d_tc_supported(p)) return conv2d_tc(p, st);
-    return conv2d_f32(p, st);   // tiny-channel layers (Cin % 4 != 0 or Cout < 16) are HBM-bound CUDA-core work
+  } else if (p->mode != CNB_MODE_F32) {
+    set_error("conv2d: unknown mode %d", p->mode);
+    return CNB_ERR_BAD_ARG;
   }
-  set_error("conv2d: unknown mode %d", p->mode);
-  return CNB_ERR_BAD_ARG;
+  // fp32 mode, and tiny-channel layers (Cin % 4 != 0 or Cout < 16) which are HBM-bound CUDA-core work
+  CNB_REQUIRE(p->in_dtype == 0, "conv2d: fp16 activations need a tensor-core eligible layer (Cin %% 8 == 0, Cout %% 16 == 0)");
+  return conv2d_f32(p, st);
 }
 
-extern "C" int cnb_groupnorm(const float* x, float* y, const float* gamma, const float* beta, int B, int HW, int C,
-                             int G, float eps, int silu, cnb_stream_t stream) {
+extern "C" int cnb_groupnorm(const float* x, void* y, const float* gamma, const float* beta, int B, int HW, int C,
+                             int G, float eps, int silu, int out_f16, cnb_stream_t stream) {
   CNB_REQUIRE(x && y && gamma && beta && B > 0 && HW > 0 && C > 0 && G > 0, "groupnorm: bad args");
-  return groupnorm(x, y, gamma, beta, B, HW, C, G, eps, silu, (cudaStream_t)stream);
+  return groupnorm(x, y, gamma, beta, B, HW, C, G, eps, silu, out_f16, (cudaStream_t)stream);
 }
 
 extern "C" int cnb_attention(const float* qkv, float* out, int B, int L, int E, int heads, int mode,

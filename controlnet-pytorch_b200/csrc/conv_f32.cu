@@ -26,6 +26,7 @@ conv_igemm_f32_kernel(const __grid_constant__ ConvArgs a) {
   constexpr int B_VEC = (BN * BK / 4 + NT - 1) / NT;
 
   const cnb_conv_params& p = a.p;
+  const float* p_in = reinterpret_cast<const float*>(p.in);
   const int M = a.M, K = a.K;
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
@@ -73,7 +74,7 @@ conv_igemm_f32_kernel(const __grid_constant__ ConvArgs a) {
           int iy = a_iy0[i] + p.dy[tap];
           int ix = a_ix0[i] + p.dx[tap];
           if ((unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W) {
-            const float* src = p.in + ((a_base[i] + (long long)iy * p.W + ix) * p.ldi + p.in_coff + c);
+            const float* src = p_in + ((a_base[i] + (long long)iy * p.W + ix) * p.ldi + p.in_coff + c);
             v = __ldg(reinterpret_cast<const float4*>(src));
           }
         }
@@ -96,7 +97,7 @@ conv_igemm_f32_kernel(const __grid_constant__ ConvArgs a) {
           int iy = oy * p.stride + p.dy[tap];
           int ix = ox * p.stride + p.dx[tap];
           if ((unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W)
-            v = __ldg(p.in + (((long long)b * p.H * p.W + (long long)iy * p.W + ix) * p.ldi + p.in_coff + c));
+            v = __ldg(p_in + (((long long)b * p.H * p.W + (long long)iy * p.W + ix) * p.ldi + p.in_coff + c));
         }
         raf[i] = v;
       }

@@ -1,7 +1,10 @@
 // tcgen05 implicit-GEMM convolution (CNB_MODE_TF32): the tensor-core path of cnb_conv2d on sm_100a.
 //
-//   GEMM view        M = B*OH*OW output pixels (tile 128 = one UMMA M),  N = Cout (tile BN in {16,32,64,128}),
-//                    K = ntaps*Cin (tile 32 fp32 = one 128-byte swizzle row).
+//   GEMM view        M = B*OH*OW output pixels (tile 128 = one UMMA M),  N = Cout (tile BN in {16,...,256}),
+//                    K = ntaps*Cin (tile = one 128-byte swizzle row: 32 fp32 (kind::tf32) or 64 fp16 (kind::f16)).
+//   operand types    fp32 activations run as kind::tf32; activations that GroupNorm already emitted as fp16
+//                    (in_dtype = 1; 10-bit mantissa like tf32, half the bytes, twice the MMA rate) run as kind::f16
+//                    against an fp16 copy of the packed weights.  Accumulation is always fp32 in TMEM.
 //   operands         A (im2col gather of the channels-last activations, zero outside the image) and W ([N][K]) are
 //                    staged into shared memory in the canonical K-major SWIZZLE_128B UMMA layout
 //                    (row r at r*128 B, 16-byte chunk c stored at chunk c ^ (r & 7)) by 128 producer threads with
@@ -13,6 +16,8 @@
 //
 // Every mbarrier wait is bounded by a clock64() guard: on expiry the CTA raises g_tc_error and drains instead of
 // hanging the GPU (cnb_tc_error_flag() reports it).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cnb {
@@ -86,9 +91,9 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
-template <bool BF16>
+template <bool HALF>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  if (BF16) {
+  if (HALF) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
@@ -130,8 +135,8 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), a/b format (bits 7..12),
 // K-major A and B (bits 15,16 = 0), N >> 3 at [17,23), M >> 4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool bf16) {
-  uint32_t fmt = bf16 ? 1u : 2u;   // F16F32Format: BF16 = 1, TF32 = 2
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool half) {
+  uint32_t fmt = half ? 0u : 2u;   // F16F32Format: F16 = 0, BF16 = 1, TF32 = 2
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -145,15 +150,22 @@ struct SmemLayout {
   static constexpr int B_STAGE_BYTES = BN * BKB;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int BAR_OFFSET = S * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // + barriers/tmem slot + 1 KB alignment slack
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 128 * 12 + 1024;   // + barriers/tmem slot + row tables + 1 KB alignment slack
 };
 
-template <int BN, int S>
+template <int BN, int S, bool HALF>
 __global__ void __launch_bounds__(160, 1)
-conv_igemm_tf32_kernel(const __grid_constant__ TcArgs a) {
+conv_igemm_tc_kernel(const __grid_constant__ TcArgs a) {
   using L = SmemLayout<BN, S>;
   constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-  constexpr uint32_t IDESC = make_idesc(BM, BN, false);
+  constexpr uint32_t IDESC = make_idesc(BM, BN, HALF);
+  constexpr int ELT = HALF ? 2 : 4;          // bytes per operand element
+  constexpr int EPC = 16 / ELT;              // elements per 16-byte chunk
+  constexpr int BKE = BKB / ELT;             // K elements per stage
+  constexpr int AROWS = BM / 16;             // A rows gathered per producer thread (8)
+  constexpr int BROWS = (BN + 15) / 16;      // W rows per producer thread
+  constexpr int OSTR = BN + 4;               // epilogue staging row stride (floats)
+  static_assert(BM * OSTR * 4 <= S * L::STAGE_BYTES, "epilogue staging must fit in the pipeline buffers");
 
   const cnb_conv_params& p = a.p;
   const int M = a.M, K = a.K;
@@ -169,13 +181,15 @@ conv_igemm_tf32_kernel(const __grid_constant__ TcArgs a) {
   uint64_t* accum_bar = empty_bar + S;                                      // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  long long* row_pix = reinterpret_cast<long long*>(smem + L::BAR_OFFSET + 256);   // [128] output pixel or -1
+  int* row_b = reinterpret_cast<int*>(row_pix + BM);                                 // [128] batch index
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
   const int m0 = blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
-  const int nkb = (K * 4 + BKB - 1) / BKB;
+  const int nkb = (K + BKE - 1) / BKE;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
@@ -194,106 +208,140 @@ conv_igemm_tf32_kernel(const __grid_constant__ TcArgs a) {
 
   if (warp < 4) {
     // ======================= producers: im2col gather (A) + weight rows (B) via cp.async =======================
-    const int r = tid;                       // tile row owned by this thread (A: pixel m0+r, B: channel n0+r)
-    const int m = m0 + r;
-    const bool m_ok = m < M;
+    // Lane mapping is chunk-major: 8 consecutive lanes fetch the 8 16-byte chunks of ONE 128-byte row, so a warp
+    // instruction touches 4 full cache lines (thread-per-row would touch 32 lines per instruction).
+    const int c = tid & 7;                   // 16-byte chunk of the K slice owned by this thread
+    const int rbase = tid >> 3;              // rows rbase + 16*j
     const int OHW = p.OH * p.OW;
-    int b = 0, oy = 0, ox = 0;
-    if (m_ok) {
-      b = m / OHW;
-      int rem = m - b * OHW;
-      oy = rem / p.OW;
-      ox = rem - oy * p.OW;
+    const char* in_base = reinterpret_cast<const char*>(p.in) + (size_t)p.in_coff * ELT;
+    const char* w_base = HALF ? reinterpret_cast<const char*>(p.weight_lp) : reinterpret_cast<const char*>(p.weight);
+    const size_t ldiB = (size_t)p.ldi * ELT;
+    const uint32_t coff = (((uint32_t)c) ^ ((uint32_t)rbase & 7u)) << 4;   // swizzled chunk offset (row & 7 == rbase & 7)
+
+    int a_pix[AROWS];          // ((b*H + iy0)*W + ix0) of the row's output pixel, or -1 when m >= M
+    int a_yx[AROWS];           // iy0 | ix0 << 16
+#pragma unroll
+    for (int j = 0; j < AROWS; ++j) {
+      const int m = m0 + rbase + 16 * j;
+      if (m < M) {
+        const int b = m / OHW;
+        const int rem = m - b * OHW;
+        const int oy = rem / p.OW;
+        const int ox = rem - oy * p.OW;
+        const int iy0 = oy * p.stride, ix0 = ox * p.stride;
+        a_pix[j] = (b * p.H + iy0) * p.W + ix0;
+        a_yx[j] = iy0 | (ix0 << 16);
+      } else {
+        a_pix[j] = -1;
+        a_yx[j] = 0;
+      }
     }
-    const int iy0 = oy * p.stride, ix0 = ox * p.stride;
-    const float* in_b = p.in + (size_t)b * p.H * p.W * p.ldi + p.in_coff;
-    const bool b_row = (r < BN);
-    const bool n_ok = b_row && (n0 + r < p.Cout);
-    const float* w_row = p.weight + (size_t)(n_ok ? (n0 + r) : 0) * K;
-    const uint32_t swz = (uint32_t)(r & 7);
-    const uint32_t a_row_off = (uint32_t)r * BKB;
-    const uint32_t b_row_off = A_STAGE_BYTES + (uint32_t)r * BKB;
 
     const int total_it = nkb + S - 1;
     for (int it = 0; it < total_it; ++it) {
+      if (it >= S - 1) {
+        cp_async_wait<(S >= 2 ? S - 2 : 0)>();   // k-block (it - S + 1) has landed (S-2 younger groups may be in flight)
+        fence_proxy_async();                     // generic-proxy smem writes -> visible to the tensor core
+        mbar_arrive(&full_bar[(it - (S - 1)) % S]);
+      }
       if (it < nkb) {
         const int s = it % S;
         if (it >= S) mbar_wait(&empty_bar[s], (uint32_t)(((it / S) - 1) & 1), abort_flag);
-        const uint32_t st_base = smem_base + (uint32_t)s * L::STAGE_BYTES;
-        const int k0 = it * (BKB / 4);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int k = k0 + c * 4;
-          const float* src = p.in;
-          uint32_t nbytes = 0;
-          if (m_ok && k < K) {
-            const int tap = k / p.Cin;
-            const int ch = k - tap * p.Cin;
-            const int iy = iy0 + p.dy[tap];
-            const int ix = ix0 + p.dx[tap];
-            if ((unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W) {
-              src = in_b + ((size_t)iy * p.W + ix) * p.ldi + ch;
-              nbytes = 16;
-            }
-          }
-          cp_async16(st_base + a_row_off + (((uint32_t)c ^ swz) << 4), src, nbytes);
+        const uint32_t st_base = smem_base + (uint32_t)s * L::STAGE_BYTES + coff;
+        const int k = it * BKE + c * EPC;        // first K element of this thread's chunk
+        const bool k_ok = k < K;
+        int dy = 0, dx = 0, ch = 0;
+        if (k_ok) {
+          const int tap = k / p.Cin;
+          ch = k - tap * p.Cin;
+          dy = p.dy[tap];
+          dx = p.dx[tap];
         }
-        if (b_row) {
+        const int dpix = dy * p.W + dx;
+        const char* src_c = in_base + (size_t)ch * ELT;
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const int k = k0 + c * 4;
-            const bool ok = n_ok && (k < K);
-            cp_async16(st_base + b_row_off + (((uint32_t)c ^ swz) << 4), ok ? (const void*)(w_row + k) : (const void*)p.weight,
-                       ok ? 16u : 0u);
+        for (int j = 0; j < AROWS; ++j) {
+          const int iy = (a_yx[j] & 0xffff) + dy;
+          const int ix = (a_yx[j] >> 16) + dx;
+          const bool ok = k_ok && a_pix[j] >= 0 && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+          const char* src = ok ? src_c + (size_t)(a_pix[j] + dpix) * ldiB : in_base;
+          cp_async16(st_base + (uint32_t)(rbase + 16 * j) * BKB, src, ok ? 16u : 0u);
+        }
+        const char* w_c = w_base + (size_t)k * ELT;
+#pragma unroll
+        for (int j = 0; j < BROWS; ++j) {
+          const int br = rbase + 16 * j;
+          if (BN % 16 == 0 || br < BN) {
+            const bool ok = k_ok && (n0 + br) < p.Cout;
+            const char* src = ok ? w_c + (size_t)(n0 + br) * K * ELT : w_base;
+            cp_async16(st_base + A_STAGE_BYTES + (uint32_t)br * BKB, src, ok ? 16u : 0u);
           }
         }
       }
       cp_async_commit();
-      if (it >= S - 1) {
-        cp_async_wait<S - 1>();       // k-block (it - S + 1) has landed
-        fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        mbar_arrive(&full_bar[(it - (S - 1)) % S]);
-      }
     }
 
-    // ======================= epilogue: TMEM -> registers -> fused adds -> channels-last store ===================
+    // ======================= epilogue =======================================================================
+    // TMEM -> registers (thread = accumulator row) -> smem staging (reusing the drained pipeline buffers) ->
+    // coalesced channels-last store with the fused + bias + time-embedding row + residual (+SiLU).
+    {
+      const int m = m0 + tid;
+      long long pix = -1;
+      int b = 0;
+      if (m < M) {
+        b = m / OHW;
+        const int rem = m - b * OHW;
+        const int oy = rem / p.OW;
+        const int ox = rem - oy * p.OW;
+        pix = ((long long)b * p.OHf + (oy * p.oy_mul + p.oy_add)) * p.OWf + (ox * p.ox_mul + p.ox_add);
+      }
+      row_pix[tid] = pix;
+      row_b[tid] = b;
+    }
     mbar_wait(accum_bar, 0, abort_flag);
     tc_fence_after();
-    long long pix = 0;
-    if (m_ok) pix = ((long long)b * p.OHf + (oy * p.oy_mul + p.oy_add)) * p.OWf + (ox * p.ox_mul + p.ox_add);
-    float* dst = p.out + pix * p.ldo + p.out_coff;
-    const float* res = p.residual ? p.residual + pix * p.ldr + p.res_coff : nullptr;
-    const float* te = p.temb ? p.temb + (size_t)(p.temb_per_sample ? b : 0) * p.temb_ld : nullptr;
+    float* stage = reinterpret_cast<float*>(smem);
     const uint32_t lane_addr = tmem_acc + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
       float v[16];
       tmem_ld16(lane_addr + (uint32_t)c0, v);
-      if (m_ok && !*abort_flag) {
-        const int nb = n0 + c0;
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          if (nb + j < p.Cout) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (p.bias) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
-              o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
-            }
-            if (te) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(te + nb + j));
-              o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
-            }
-            if (res) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(res + nb + j));
-              o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
-            }
-            if (p.act == 1) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
-            *reinterpret_cast<float4*>(dst + nb + j) = o;
+      float4* d = reinterpret_cast<float4*>(stage + (size_t)tid * OSTR + c0);
+      d[0] = make_float4(v[0], v[1], v[2], v[3]);
+      d[1] = make_float4(v[4], v[5], v[6], v[7]);
+      d[2] = make_float4(v[8], v[9], v[10], v[11]);
+      d[3] = make_float4(v[12], v[13], v[14], v[15]);
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, 128;" ::: "memory");     // the 4 epilogue warps only
+    if (!*abort_flag) {
+      constexpr int C4 = BN / 4;                       // float4 columns per row
+#pragma unroll 1
+      for (int idx = tid; idx < BM * C4; idx += NUM_PRODUCERS) {
+        const int row = idx / C4;
+        const int c4 = idx - row * C4;
+        const long long pix = row_pix[row];
+        const int n = n0 + c4 * 4;
+        if (pix >= 0 && n < p.Cout) {
+          float4 o = *reinterpret_cast<const float4*>(stage + (size_t)row * OSTR + c4 * 4);
+          if (p.bias) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
           }
+          if (p.temb) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(
+                p.temb + (size_t)(p.temb_per_sample ? row_b[row] : 0) * p.temb_ld + n));
+            o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+          }
+          if (p.residual) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p.residual + pix * p.ldr + p.res_coff + n));
+            o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+          }
+          if (p.act == 1) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+          *reinterpret_cast<float4*>(p.out + pix * p.ldo + p.out_coff + n) = o;
         }
       }
     }
-    tc_fence_before();
   } else {
     // ======================= MMA issuer (warp 4): one elected lane drives the tensor core ======================
     for (int kb = 0; kb < nkb; ++kb) {
@@ -306,8 +354,8 @@ conv_igemm_tf32_kernel(const __grid_constant__ TcArgs a) {
         const uint64_t bdesc = make_desc_sw128(a_addr + A_STAGE_BYTES);
 #pragma unroll
         for (int k = 0; k < BKB / 32; ++k) {
-          // advance 32 bytes (8 tf32) along K inside the swizzle atom: +2 in the (addr >> 4) field
-          umma<false>(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kb | k) ? 1u : 0u);
+          // advance 32 bytes (8 tf32 / 16 fp16) along K inside the swizzle atom: +2 in the (addr >> 4) field
+          umma<HALF>(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kb | k) ? 1u : 0u);
         }
         umma_commit(&empty_bar[s]);              // frees the smem stage once these MMAs have read it
         if (kb == nkb - 1) umma_commit(accum_bar);   // accumulator complete -> epilogue
@@ -324,31 +372,49 @@ conv_igemm_tf32_kernel(const __grid_constant__ TcArgs a) {
   }
 }
 
-template <int BN, int S>
+template <int BN, int S, bool HALF>
 static int launch_tc(const TcArgs& a, cudaStream_t st) {
   using L = SmemLayout<BN, S>;
   static bool attr_set = false;
   if (!attr_set) {
-    CNB_CUDA(cudaFuncSetAttribute(conv_igemm_tf32_kernel<BN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    CNB_CUDA(cudaFuncSetAttribute(conv_igemm_tc_kernel<BN, S, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_set = true;
   }
   dim3 grid(ceil_div(a.M, BM), ceil_div(a.p.Cout, BN));
-  conv_igemm_tf32_kernel<BN, S><<<grid, 160, L::TOTAL, st>>>(a);
+  conv_igemm_tc_kernel<BN, S, HALF><<<grid, 160, L::TOTAL, st>>>(a);
   CNB_LAUNCH_CHECK();
   return CNB_OK;
+}
+
+template <bool HALF>
+static int dispatch_tc(const TcArgs& a, cudaStream_t st) {
+  const int cout = a.p.Cout;
+  static int deep = -1;
+  if (deep < 0) {
+    const char* e = getenv("CNB_TC_DEEP");
+    deep = e ? atoi(e) : 1;
+  }
+  if (cout % 256 == 0) return launch_tc<256, 4, HALF>(a, st);
+  if (cout % 128 == 0) return deep ? launch_tc<128, 6, HALF>(a, st) : launch_tc<128, 3, HALF>(a, st);
+  if (cout % 64 == 0) return launch_tc<64, 4, HALF>(a, st);
+  if (cout % 32 == 0) return launch_tc<32, 4, HALF>(a, st);
+  return launch_tc<16, 4, HALF>(a, st);
 }
 
 }  // namespace tc
 
 bool conv2d_tc_supported(const cnb_conv_params* p) {
-  if (p->mode != CNB_MODE_TF32) return false;   // bf16 operands: next round (activations are fp32 in HBM today)
-  if (p->Cin % 4 || p->ldi % 4 || p->in_coff % 4) return false;
+  if (p->mode == CNB_MODE_F32) return false;
+  const bool half = p->in_dtype == 1;
+  const int epc = half ? 8 : 4;
+  if (half && !p->weight_lp) return false;
+  if (p->Cin % epc || p->ldi % epc || p->in_coff % epc) return false;
   if (p->Cout < 16 || p->Cout % 16) return false;
   if (p->ldo % 4 || p->out_coff % 4) return false;
   if (p->residual && (p->ldr % 4 || p->res_coff % 4)) return false;
   if (p->temb && (p->temb_ld % 4)) return false;
-  if (((uintptr_t)p->in | (uintptr_t)p->weight | (uintptr_t)p->out | (uintptr_t)p->bias | (uintptr_t)p->temb |
-       (uintptr_t)p->residual) & 15)
+  if (((uintptr_t)p->in | (uintptr_t)p->weight | (uintptr_t)p->weight_lp | (uintptr_t)p->out | (uintptr_t)p->bias |
+       (uintptr_t)p->temb | (uintptr_t)p->residual) & 15)
     return false;
   return true;
 }
@@ -358,10 +424,7 @@ int conv2d_tc(const cnb_conv_params* p, cudaStream_t st) {
   a.p = *p;
   a.M = p->B * p->OH * p->OW;
   a.K = p->ntaps * p->Cin;
-  if (p->Cout % 128 == 0) return tc::launch_tc<128, 3>(a, st);
-  if (p->Cout % 64 == 0) return tc::launch_tc<64, 4>(a, st);
-  if (p->Cout % 32 == 0) return tc::launch_tc<32, 4>(a, st);
-  return tc::launch_tc<16, 4>(a, st);
+  return p->in_dtype == 1 ? tc::dispatch_tc<true>(a, st) : tc::dispatch_tc<false>(a, st);
 }
 
 }  // namespace cnb

@@ -1,6 +1,8 @@
 // Small / memory-bound kernels of the path: time embedding, t-embedding MLP rows, scheduler step (bit-exact fp32
 // restatement of scheduler/linear_noise_scheduler.py:58-77 with optional fused Philox noise), EDM scalings,
 // NCHW <-> channels-last plumbing and one-time weight packers.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace cnb {
@@ -286,6 +288,11 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
   if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
 }
 
+__global__ void cast_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2half_rn(src[i]);
+}
+
 }  // namespace cnb
 
 // ================================================================================================
@@ -425,6 +432,13 @@ extern "C" int cnb_pack_convT_weight(const float* w, float* dst, int I, int O, i
 extern "C" int cnb_cast_bf16(const float* src, void* dst, long long n, cnb_stream_t s) {
   CNB_REQUIRE(n > 0, "cast_bf16: n=%lld", n);
   cast_bf16_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)s>>>(src, (__nv_bfloat16*)dst, n);
+  CNB_LAUNCH_CHECK();
+  return CNB_OK;
+}
+
+extern "C" int cnb_cast_f16(const float* src, void* dst, long long n, cnb_stream_t s) {
+  CNB_REQUIRE(n > 0, "cast_f16: n=%lld", n);
+  cast_f16_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)s>>>(src, (__half*)dst, n);
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }

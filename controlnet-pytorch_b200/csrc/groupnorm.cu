@@ -4,13 +4,28 @@
 // sweeps of the slab are L1/L2 hits (a slab is at most a few hundred KB), so DRAM sees one read + one write.
 // Per-thread column ownership (thread <-> fixed 4 channels) makes the reduction a deterministic tree:
 // registers -> smem [rows][C] -> per-channel -> per-group.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace cnb {
 
-template <bool SILU>
+template <bool HALF> struct OutVec;
+template <> struct OutVec<false> {
+  using type = float4;
+  static __device__ __forceinline__ float4 pack(float4 v) { return v; }
+};
+template <> struct OutVec<true> {
+  using type = uint2;   // 4 x fp16
+  static __device__ __forceinline__ uint2 pack(float4 v) {
+    __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    return make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+};
+
+template <bool SILU, bool HALF>
 __global__ void __launch_bounds__(1024)
-groupnorm_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ gamma,
+groupnorm_nhwc_kernel(const float* __restrict__ x, void* __restrict__ y, const float* __restrict__ gamma,
                       const float* __restrict__ beta, int HW, int C, int G, float eps) {
   extern __shared__ float sm[];
   const int C4 = C >> 2;
@@ -26,7 +41,8 @@ groupnorm_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
   const int r0 = tid / C4;
   const int cg = C / G;
   const float4* xs = reinterpret_cast<const float4*>(x + (size_t)blockIdx.x * HW * C);
-  float4* ys = reinterpret_cast<float4*>(y + (size_t)blockIdx.x * HW * C);
+  using OV = OutVec<HALF>;
+  typename OV::type* ys = reinterpret_cast<typename OV::type*>(y) + (size_t)blockIdx.x * HW * C4;
   const float inv_n = 1.0f / (float)(cg * HW);
 
   // ---- pass 1: per-channel sums -> group means
@@ -123,16 +139,16 @@ groupnorm_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, const 
     float4 v1 = xs[(size_t)(pidx + R) * C4 + col];
     float4 v2 = xs[(size_t)(pidx + 2 * R) * C4 + col];
     float4 v3 = xs[(size_t)(pidx + 3 * R) * C4 + col];
-    ys[(size_t)pidx * C4 + col] = apply(v0);
-    ys[(size_t)(pidx + R) * C4 + col] = apply(v1);
-    ys[(size_t)(pidx + 2 * R) * C4 + col] = apply(v2);
-    ys[(size_t)(pidx + 3 * R) * C4 + col] = apply(v3);
+    ys[(size_t)pidx * C4 + col] = OV::pack(apply(v0));
+    ys[(size_t)(pidx + R) * C4 + col] = OV::pack(apply(v1));
+    ys[(size_t)(pidx + 2 * R) * C4 + col] = OV::pack(apply(v2));
+    ys[(size_t)(pidx + 3 * R) * C4 + col] = OV::pack(apply(v3));
   }
-  for (; pidx < HW; pidx += R) ys[(size_t)pidx * C4 + col] = apply(xs[(size_t)pidx * C4 + col]);
+  for (; pidx < HW; pidx += R) ys[(size_t)pidx * C4 + col] = OV::pack(apply(xs[(size_t)pidx * C4 + col]));
 }
 
-int groupnorm(const float* x, float* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
-              float eps, int silu, cudaStream_t st) {
+int groupnorm(const float* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
+              float eps, int silu, int out_f16, cudaStream_t st) {
   CNB_REQUIRE(C % 4 == 0 && C % G == 0 && C / 4 <= 1024, "groupnorm: C=%d G=%d unsupported", C, G);
   const int C4 = C / 4;
   int R = 512 / C4;
@@ -141,10 +157,14 @@ int groupnorm(const float* x, float* y, const float* gamma, const float* beta, i
   const int NT = R * C4;
   size_t smem = ((size_t)R * C + C + 2 * G) * sizeof(float);
   CNB_REQUIRE(smem <= 48 * 1024, "groupnorm: smem %zu too large", smem);
-  if (silu)
-    groupnorm_nhwc_kernel<true><<<B, NT, smem, st>>>(x, y, gamma, beta, HW, C, G, eps);
+  if (silu && out_f16)
+    groupnorm_nhwc_kernel<true, true><<<B, NT, smem, st>>>(x, y, gamma, beta, HW, C, G, eps);
+  else if (silu)
+    groupnorm_nhwc_kernel<true, false><<<B, NT, smem, st>>>(x, y, gamma, beta, HW, C, G, eps);
+  else if (out_f16)
+    groupnorm_nhwc_kernel<false, true><<<B, NT, smem, st>>>(x, y, gamma, beta, HW, C, G, eps);
   else
-    groupnorm_nhwc_kernel<false><<<B, NT, smem, st>>>(x, y, gamma, beta, HW, C, G, eps);
+    groupnorm_nhwc_kernel<false, false><<<B, NT, smem, st>>>(x, y, gamma, beta, HW, C, G, eps);
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }

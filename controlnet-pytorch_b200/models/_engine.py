@@ -54,6 +54,21 @@ def packed_conv(param, mode):
     return _cached(param, ("conv", r), lambda: ops.pack_conv_weight(param, r))
 
 
+def packed_conv_f16(param, mode):
+    """fp16 copy of the packed (unrounded) weights: B operand of the kind::f16 convolution."""
+    return _cached(param, ("conv_f16",), lambda: ops.cast_f16(ops.pack_conv_weight(param, False)))
+
+
+def use_f16(mode, cin, cout):
+    """GroupNorm -> conv pairs run with fp16 operands in the tensor-core mode (same 10-bit mantissa as tf32, half the
+    bytes, twice the MMA rate) when the layer is tensor-core eligible.  CNB_F16=0 keeps everything tf32."""
+    return mode != rt.MODE_F32 and _F16_ENABLED and cin % 8 == 0 and cout % 16 == 0
+
+
+import os as _os
+_F16_ENABLED = _os.environ.get("CNB_F16", "1") != "0"
+
+
 def packed_convT(param, mode):
     r = mode != rt.MODE_F32 and _tc_shape(param.shape[1], param.shape[0])
     return _cached(param, ("convT", r), lambda: ops.pack_convT_weight(param, r))
@@ -153,24 +168,29 @@ class ResAttnStack(nn.Module):
     def _resnet(self, j, x, temb, mode):
         first, second = self.resnet_conv_first[j], self.resnet_conv_second[j]
         cout = first[2].out_channels
-        h = ops.groupnorm(x, raw(first[0].weight), raw(first[0].bias), self._groups, silu=True)
+        h16 = use_f16(mode, first[2].in_channels, cout)
+        h = ops.groupnorm(x, raw(first[0].weight), raw(first[0].bias), self._groups, silu=True, out_f16=h16)
         if temb is not None and self.t_emb_dim is not None:
             trow, tld, tps = temb.row(self, j)
         else:
             trow, tld, tps = None, 0, False
         h = ops.conv(h, packed_conv(first[2].weight, mode), "3x3", cout, bias=raw(first[2].bias),
-                     temb=trow, temb_ld=tld, temb_per_sample=tps, mode=mode)
-        h = ops.groupnorm(h, raw(second[0].weight), raw(second[0].bias), self._groups, silu=True)
+                     temb=trow, temb_ld=tld, temb_per_sample=tps, mode=mode,
+                     weight_lp=packed_conv_f16(first[2].weight, mode) if h16 else None)
+        h16 = use_f16(mode, cout, cout)
+        h = ops.groupnorm(h, raw(second[0].weight), raw(second[0].bias), self._groups, silu=True, out_f16=h16)
         rc = self.residual_input_conv[j]
         r = ops.conv(x, packed_conv(rc.weight, mode), "1x1", cout, bias=raw(rc.bias), mode=mode)
         return ops.conv(h, packed_conv(second[2].weight, mode), "3x3", cout, bias=raw(second[2].bias),
-                        residual=r, mode=mode)
+                        residual=r, mode=mode, weight_lp=packed_conv_f16(second[2].weight, mode) if h16 else None)
 
     def _attention(self, j, x, mode):
         norm, att = self.attention_norms[j], self.attentions[j]
         E = att.embed_dim
-        a = ops.groupnorm(x, raw(norm.weight), raw(norm.bias), self._groups, silu=False)
-        qkv = ops.conv(a, packed_conv(att.in_proj_weight, mode), "1x1", 3 * E, bias=raw(att.in_proj_bias), mode=mode)
+        h16 = use_f16(mode, E, 3 * E)
+        a = ops.groupnorm(x, raw(norm.weight), raw(norm.bias), self._groups, silu=False, out_f16=h16)
+        qkv = ops.conv(a, packed_conv(att.in_proj_weight, mode), "1x1", 3 * E, bias=raw(att.in_proj_bias), mode=mode,
+                       weight_lp=packed_conv_f16(att.in_proj_weight, mode) if h16 else None)
         o = ops.attention(qkv, att.num_heads, mode=mode)
         return ops.conv(o, packed_conv(att.out_proj.weight, mode), "1x1", E, bias=raw(att.out_proj.bias),
                         residual=x, mode=mode)

@@ -47,11 +47,14 @@ def empty(*shape, device, dtype=torch.float32):
 
 
 def conv(x, weight, kind, cout, *, bias=None, temb=None, temb_ld=0, temb_per_sample=False, residual=None,
-         res_coff=0, act=0, out=None, out_coff=0, in_coff=0, cin=None, mode=None, phase=None):
+         res_coff=0, act=0, out=None, out_coff=0, in_coff=0, cin=None, mode=None, phase=None, weight_lp=None):
     """Launch cnb_conv2d.  `x` is (B, H, W, ldi); `weight` is the packed [cout][ntaps][cin] tensor.
     kind in {"1x1","3x3","3x3s2","4x4s2"} or phase=(py,px) for a ConvTranspose2d phase (then `out` is required
     and has spatial size (2H, 2W))."""
-    rt.require_cuda(x, weight, bias, temb, residual, out)
+    rt.require_cuda(x, weight, bias, temb, residual, out, weight_lp)
+    half = x.dtype == torch.float16
+    if half and weight_lp is None:
+        raise rt.CnbError("fp16 activations need the fp16 copy of the packed weights (weight_lp)")
     B, H, W, ldi = x.shape
     cin = ldi - in_coff if cin is None else cin
     if phase is not None:
@@ -69,7 +72,8 @@ def conv(x, weight, kind, cout, *, bias=None, temb=None, temb_ld=0, temb_per_sam
         out = torch.empty((B, OHf, OWf, cout), device=x.device, dtype=torch.float32)
     assert out.shape[0] == B and out.shape[1] == OHf and out.shape[2] == OWf, (out.shape, (B, OHf, OWf))
     p = rt.ConvParams()
-    p.inp, p.weight, p.weight_lp = x.data_ptr(), weight.data_ptr(), 0
+    p.inp, p.weight, p.weight_lp = x.data_ptr(), weight.data_ptr(), rt.ptr(weight_lp)
+    p.in_dtype = 1 if half else 0
     p.bias, p.temb, p.residual, p.out = rt.ptr(bias), rt.ptr(temb), rt.ptr(residual), out.data_ptr()
     p.B, p.H, p.W, p.Cin, p.ldi, p.in_coff = B, H, W, cin, ldi, in_coff
     p.OH, p.OW, p.OHf, p.OWf = OH, OW, OHf, OWf
@@ -86,12 +90,20 @@ def conv(x, weight, kind, cout, *, bias=None, temb=None, temb_ld=0, temb_per_sam
     return out
 
 
-def groupnorm(x, gamma, beta, groups, silu, eps=1e-5):
+def groupnorm(x, gamma, beta, groups, silu, eps=1e-5, out_f16=False):
+    """out_f16: emit the normalised activations as fp16, the operand type of the kind::f16 convolution after it."""
     rt.require_cuda(x, gamma, beta)
     B, H, W, C = x.shape
-    y = torch.empty_like(x)
+    y = torch.empty((B, H, W, C), device=x.device, dtype=torch.float16 if out_f16 else torch.float32)
     rt.check(rt.lib().cnb_groupnorm(x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, H * W, C,
-                                    groups, eps, 1 if silu else 0, rt.stream()))
+                                    groups, eps, 1 if silu else 0, 1 if out_f16 else 0, rt.stream()))
+    return y
+
+
+def cast_f16(x):
+    rt.require_cuda(x)
+    y = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    rt.check(rt.lib().cnb_cast_f16(x.data_ptr(), y.data_ptr(), x.numel(), rt.stream()))
     return y
 
 

@@ -30,12 +30,13 @@ class ConvParams(ctypes.Structure):
         ("stride", ctypes.c_int32), ("ntaps", ctypes.c_int32),
         ("dy", ctypes.c_int8 * MAX_TAPS), ("dx", ctypes.c_int8 * MAX_TAPS),
         ("temb_ld", ctypes.c_int32), ("temb_per_sample", ctypes.c_int32),
-        ("act", ctypes.c_int32), ("mode", ctypes.c_int32),
+        ("act", ctypes.c_int32), ("mode", ctypes.c_int32), ("in_dtype", ctypes.c_int32),
     ]
 
 
 _SIGS = {
     "cnb_abi_version": (c_int, []),
+    "cnb_sizeof_conv_params": (c_int, []),
     "cnb_last_error": (ctypes.c_char_p, []),
     "cnb_launch_count": (c_ll, []),
     "cnb_reset_launch_count": (None, []),
@@ -44,8 +45,9 @@ _SIGS = {
     "cnb_pack_conv_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "cnb_pack_convT_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "cnb_cast_bf16": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
+    "cnb_cast_f16": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
     "cnb_groupnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int,
-                              c_void_p]),
+                              c_int, c_void_p]),
     "cnb_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "cnb_linear_small": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p]),
@@ -89,6 +91,9 @@ def lib():
         fn = getattr(handle, name)
         fn.restype = res
         fn.argtypes = args
+    if handle.cnb_sizeof_conv_params() != ctypes.sizeof(ConvParams):
+        raise CnbError("ConvParams mirror is out of sync with include/cnb200.h (%d vs %d bytes)" % (
+            ctypes.sizeof(ConvParams), handle.cnb_sizeof_conv_params()))
     _lib = handle
     return _lib
 

@@ -134,11 +134,25 @@ def sample_data_parallel(model, scheduler, shape, hint_fn, steps=None, seed=0, g
     xt, x0 = smp.sample(x_T, hint_fn(lo, hi), steps=steps, elem_offset=lo * per)
     if not gather or world == 1:
         return xt
-    sizes = [shard_bounds(B, world, r) for r in range(world)]
-    if all(b - a == sizes[0][1] - sizes[0][0] for a, b in sizes):
-        out = torch.empty((B,) + tuple(shape[1:]), device=dev, dtype=xt.dtype)
-        dist.all_gather_into_tensor(out, xt.contiguous(), group=group)
+    return gather_shards(xt, B, group)
+
+
+def gather_shards(x_local, total, group=None):
+    """The one exchange step of the job: concatenate every rank's contiguous batch shard (shard_bounds order).
+    all_gather_into_tensor when the shards are equal, padded all_gather otherwise.  Backend-agnostic (NCCL on the
+    GPUs; the world_size-2 gloo test drives it on CPU tensors)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    sizes = [b - a for a, b in (shard_bounds(total, world, r) for r in range(world))]
+    tail = tuple(x_local.shape[1:])
+    x_local = x_local.contiguous()
+    if all(n == sizes[0] for n in sizes):
+        out = torch.empty((total,) + tail, device=x_local.device, dtype=x_local.dtype)
+        dist.all_gather_into_tensor(out, x_local, group=group)
         return out
-    parts = [torch.empty((b - a,) + tuple(shape[1:]), device=dev, dtype=xt.dtype) for a, b in sizes]
-    dist.all_gather(parts, xt.contiguous(), group=group)
-    return torch.cat(parts, dim=0)
+    mx = max(sizes)
+    padded = torch.zeros((mx,) + tail, device=x_local.device, dtype=x_local.dtype)
+    padded[: x_local.shape[0]] = x_local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)
+    return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)

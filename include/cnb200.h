@@ -40,6 +40,8 @@ extern "C" {
 typedef void* cnb_stream_t; /* cudaStream_t */
 
 int cnb_abi_version(void);
+/* sizeof(cnb_conv_params) as compiled into the library (bindings assert their mirror struct against it). */
+int cnb_sizeof_conv_params(void);
 const char* cnb_last_error(void);
 /* Number of kernels this library has launched since load / last reset (bench.py's gpu_launches). */
 long long cnb_launch_count(void);
@@ -60,9 +62,9 @@ int cnb_has_tcgen05(void);
  * (controlnet.py:184,207,216-218).
  */
 typedef struct cnb_conv_params {
-  const float* in;        /* [B, H, W, ldi]                                   */
+  const void* in;         /* [B, H, W, ldi] fp32 (in_dtype 0) or fp16 (in_dtype 1) */
   const float* weight;    /* [Cout][ntaps][Cin] fp32 (cnb_pack_* output)      */
-  const void* weight_lp;  /* optional bf16 copy of `weight` for CNB_MODE_BF16 */
+  const void* weight_lp;  /* fp16 copy of `weight`, required when in_dtype==1 */
   const float* bias;      /* [Cout] or NULL                                   */
   const float* temb;      /* [(B|1), temb_ld] or NULL                         */
   const float* residual;  /* [B, OHf, OWf, ldr] or NULL                       */
@@ -80,6 +82,7 @@ typedef struct cnb_conv_params {
   int32_t temb_ld, temb_per_sample;
   int32_t act;            /* 0 = none, 1 = SiLU on the result                 */
   int32_t mode;           /* CNB_MODE_*                                       */
+  int32_t in_dtype;       /* 0 = fp32 activations, 1 = fp16 activations (tensor-core modes only) */
 } cnb_conv_params;
 
 int cnb_conv2d(const cnb_conv_params* p, cnb_stream_t stream);
@@ -90,16 +93,18 @@ int cnb_pack_conv_weight(const float* w_oihw, float* dst, int O, int I, int KH, 
 /* ConvTranspose2d weight (I, O, 4, 4), stride 2, pad 1 -> [4 phases (py*2+px)][O][4 taps (a*2+b)][I]
  * with the taps of SURVEY.md Appendix F: T(0) = {(ky=1,dy=0),(ky=3,dy=-1)}, T(1) = {(ky=0,dy=+1),(ky=2,dy=0)}. */
 int cnb_pack_convT_weight(const float* w_iohw, float* dst, int I, int O, int round_tf32, cnb_stream_t stream);
-/* fp32 -> bf16 (round to nearest even) */
+/* fp32 -> bf16 / fp16 (round to nearest even) */
 int cnb_cast_bf16(const float* src, void* dst, long long n, cnb_stream_t stream);
+int cnb_cast_f16(const float* src, void* dst, long long n, cnb_stream_t stream);
 
 /*
- * GroupNorm (+ optional SiLU) over channels-last activations: x, y are [B, HW, C] contiguous.
+ * GroupNorm (+ optional SiLU) over channels-last activations: x, y are [B, HW, C] contiguous; y is fp32, or fp16
+ * when out_f16 != 0 (the operand type of the kind::f16 tensor-core convolution that consumes it).
  * Replaces nn.GroupNorm(G, C) [+ nn.SiLU] (unet_base.py:47-48,65-66,74,104-105,338 + :372; eps = 1e-5,
  * biased variance, per-channel affine).
  */
-int cnb_groupnorm(const float* x, float* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
-                  float eps, int silu, cnb_stream_t stream);
+int cnb_groupnorm(const float* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
+                  float eps, int silu, int out_f16, cnb_stream_t stream);
 
 /*
  * Self-attention core on packed projections: qkv is [B, L, 3E] (q | k | v, heads split along E), out is [B, L, E].

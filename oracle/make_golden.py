@@ -146,6 +146,24 @@ def main():
                 a, b = s.sample_prev_timestep(xt, eps, torch.as_tensor(t))
             rec[f"prev_{t}"], rec[f"x0_{t}"] = a.numpy(), b.numpy()
         np.savez_compressed(os.path.join(OUT, f"scheduler_{name}.npz"), **rec)
+    # ---- state_dict layout manifest (key -> shape) of every reference module on the path
+    import json
+    from models.unet_cond_base import Unet as RefUnetLDM
+    from models.consistency_controlnet_distilled import ConsistencyControlNetDistilled as RefConsD
+    from models.distribution_matching_controlnet import DistributionMatchingControlNetDistilled as RefDMD
+    man = {}
+    for tag, mod in (("controlnet_mnist", RefControlNet(syn.MNIST_PARAMS)),
+                     ("unet_mnist", RefUnet(syn.MNIST_PARAMS)),
+                     ("unet_mnist_noup", RefUnet(syn.MNIST_PARAMS, use_up=False)),
+                     ("controlnet_ldm_tiny", RefControlNetLDM(4, syn.TINY_LDM_PARAMS, down_sample_factor=8)),
+                     ("unet_ldm_tiny", RefUnetLDM(4, syn.TINY_LDM_PARAMS)),
+                     ("consistency_mnist", RefCons(syn.MNIST_PARAMS)),
+                     ("dm_mnist", RefDM(syn.MNIST_PARAMS)),
+                     ("consistency_distilled_tiny", RefConsD(syn.TINY_PARAMS)),
+                     ("dm_distilled_tiny", RefDMD(syn.TINY_PARAMS, "missing.pth", device=None))):
+        man[tag] = {k: list(v.shape) for k, v in mod.state_dict().items()}
+    with open(os.path.join(OUT, "state_dict_manifest.json"), "w") as f:
+        json.dump(man, f)
     print("done ->", OUT)
 
 

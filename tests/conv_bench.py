@@ -40,22 +40,30 @@ if what in ("conv", "all"):
               ("3x3", 64, 128, 14), ("3x3", 32, 64, 28), ("3x3", 16, 16, 28), ("3x3", 64, 16, 28),
               ("1x1", 64, 192, 28), ("1x1", 64, 64, 28), ("1x1", 256, 768, 7), ("1x1", 256, 256, 7),
               ("4x4s2", 64, 64, 28), ("3x3", 128, 32, 28)]
-    for mode in (rt.MODE_TF32, rt.MODE_F32):
+    variants = [("f16", rt.MODE_TF32, True), ("tf32", rt.MODE_TF32, False)]
+    if os.environ.get("CB_FP32", "0") == "1":
+        variants.append(("fp32", rt.MODE_F32, False))
+    for name, mode, half in variants:
         for kind, cin, cout, hw in shapes:
             k = {"3x3": 9, "1x1": 1, "4x4s2": 16}[kind]
+            if half and (cin % 8 or cout % 16):
+                continue
             x = torch.randn(B, hw, hw, cin, device="cuda")
             w = torch.randn(cout, k, cin, device="cuda") / math.sqrt(k * cin)
+            wl = ops.cast_f16(w) if half else None
+            if half:
+                x = x.half()
             bias = torch.randn(cout, device="cuda")
             oh = ops.out_size(kind, hw)
             out = torch.empty(B, oh, oh, cout, device="cuda")
-            ms = timeit(lambda: ops.conv(x, w, kind, cout, bias=bias, out=out, mode=mode))
+            ms = timeit(lambda: ops.conv(x, w, kind, cout, bias=bias, out=out, mode=mode, weight_lp=wl))
             fl = 2.0 * B * oh * oh * k * cin * cout
-            by = 4.0 * (x.numel() + out.numel() + w.numel())
-            print(f"conv[{rt.mode_name(mode)}] {kind} {cin}->{cout} @{hw}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:8.1f} TFLOP/s  "
+            by = x.numel() * x.element_size() + 4.0 * out.numel() + w.numel() * (2 if half else 4)
+            print(f"conv[{name}] {kind} {cin}->{cout} @{hw}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:8.1f} TFLOP/s  "
                   f"{by / ms / 1e6:8.1f} GB/s(min-traffic)", flush=True)
 
 if what in ("attn", "all"):
-    for mode in (rt.MODE_TF32, rt.MODE_F32):
+    for mode in ((rt.MODE_TF32, rt.MODE_F32) if os.environ.get("CB_FP32", "0") == "1" else (rt.MODE_TF32,)):
         for L, E, heads in [(784, 64, 4), (784, 16, 4), (196, 128, 4), (196, 32, 4), (49, 256, 4), (49, 128, 4), (49, 64, 4)]:
             side = int(math.isqrt(L))
             qkv = torch.randn(B, side, side, 3 * E, device="cuda")

@@ -82,6 +82,25 @@ def test_conv(pk, kind, B, Cin, Cout, H, W, mode, tol):
         assert rt.lib().cnb_tc_error_flag() == 0
 
 
+@pytest.mark.parametrize("kind,B,Cin,Cout,H,W", [c for c in CONV_CASES if c[2] % 8 == 0 and c[3] % 16 == 0] +
+                         [("3x3", 2, 64, 256, 7, 7), ("3x3", 1, 512, 512, 8, 8), ("1x1", 3, 8, 16, 6, 6)])
+def test_conv_f16_operands(pk, kind, B, Cin, Cout, H, W):
+    """kind::f16 tensor-core path: fp16 activations (as GroupNorm emits them) x fp16 weights, fp32 accumulate."""
+    ops, rt = pk
+    k = {"3x3": 3, "1x1": 1, "4x4s2": 4, "3x3s2": 3}[kind]
+    x, w, b = rnd(B, Cin, H, W, seed=1), rnd(Cout, Cin, k, k, seed=2) / math.sqrt(Cin * k * k), rnd(Cout, seed=3)
+    res = rnd(*_conv_ref(kind, x, w, b).shape, seed=5)
+    want = _conv_ref(kind, x, w, b) + res
+    want_q = _conv_ref(kind, x.half().float(), w.half().float(), b) + res     # same operand rounding, exact math
+    wp = ops.pack_conv_weight(w.cuda(), round_tf32=False)
+    got = ops.conv(nhwc(x).cuda().half(), wp, kind, Cout, bias=b.cuda(), residual=nhwc(res).cuda(), mode=rt.MODE_TF32,
+                   weight_lp=ops.cast_f16(wp))
+    assert got.dtype == torch.float32
+    assert rel_l2(nchw(got.cpu()), want_q) < 5e-6
+    assert rel_l2(nchw(got.cpu()), want) < 1e-3
+    assert rt.lib().cnb_tc_error_flag() == 0
+
+
 @pytest.mark.parametrize("mode,tol", [("fp32", 2e-6), ("tf32", 2e-3)])
 @pytest.mark.parametrize("B,C,H,W", [(2, 32, 7, 7), (1, 64, 14, 14), (3, 16, 5, 3)])
 def test_conv_transpose_into_concat(pk, B, C, H, W, mode, tol):
@@ -111,6 +130,9 @@ def test_groupnorm(pk, B, C, G, H, W, silu):
         want = F.silu(want)
     got = ops.groupnorm(nhwc(x).cuda(), g.cuda(), b.cuda(), G, silu)
     assert rel_l2(nchw(got.cpu()), want) < 3e-6
+    got16 = ops.groupnorm(nhwc(x).cuda(), g.cuda(), b.cuda(), G, silu, out_f16=True)
+    assert got16.dtype == torch.float16
+    assert rel_l2(nchw(got16.float().cpu()), want) < 6e-4
 
 
 @pytest.mark.parametrize("B,L,E,heads", [(2, 784, 64, 4), (2, 784, 16, 4), (3, 196, 128, 4), (2, 49, 256, 4),
