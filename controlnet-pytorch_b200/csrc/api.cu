@@ -23,6 +23,8 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int conv2d_f32(const cnb_conv_params* p, cudaStream_t st);
 int conv2d_tc(const cnb_conv_params* p, cudaStream_t st);
 bool conv2d_tc_supported(const cnb_conv_params* p);
+int conv2d_tma(const cnb_conv_params* p, cudaStream_t st);
+bool conv2d_tma_supported(const cnb_conv_params* p);
 int groupnorm(const float* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
               float eps, int silu, int out_f16, cudaStream_t st);
 int attention_f32(const float* qkv, float* out, int B, int L, int E, int heads, cudaStream_t st);
@@ -67,13 +69,16 @@ extern "C" int cnb_conv2d(const cnb_conv_params* p, cnb_stream_t stream) {
               "conv2d: output mapping exceeds the output tensor");
   cudaStream_t st = (cudaStream_t)stream;
   CNB_REQUIRE(p->in_dtype == 0 || p->in_dtype == 1, "conv2d: in_dtype=%d", p->in_dtype);
+  CNB_REQUIRE(p->out_dtype == 0 || p->out_dtype == 1, "conv2d: out_dtype=%d", p->out_dtype);
   if (p->mode == CNB_MODE_TF32 || p->mode == CNB_MODE_BF16) {
-    if (conv2d_tc_supported(p)) return conv2d_tc(p, st);
+    if (conv2d_tma_supported(p)) return conv2d_tma(p, st);     // TMA-im2col fed persistent tcgen05 kernel
+    if (conv2d_tc_supported(p)) return conv2d_tc(p, st);       // cp.async-gather tcgen05 kernel (narrow Cin)
   } else if (p->mode != CNB_MODE_F32) {
     set_error("conv2d: unknown mode %d", p->mode);
     return CNB_ERR_BAD_ARG;
   }
   // fp32 mode, and tiny-channel layers (Cin % 4 != 0 or Cout < 16) which are HBM-bound CUDA-core work
+  CNB_REQUIRE(p->out_dtype == 0, "conv2d: fp16 output needs a tensor-core eligible layer");
   CNB_REQUIRE(p->in_dtype == 0, "conv2d: fp16 activations need a tensor-core eligible layer (Cin %% 8 == 0, Cout %% 16 == 0)");
   return conv2d_f32(p, st);
 }

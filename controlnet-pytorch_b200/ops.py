@@ -47,7 +47,8 @@ def empty(*shape, device, dtype=torch.float32):
 
 
 def conv(x, weight, kind, cout, *, bias=None, temb=None, temb_ld=0, temb_per_sample=False, residual=None,
-         res_coff=0, act=0, out=None, out_coff=0, in_coff=0, cin=None, mode=None, phase=None, weight_lp=None):
+         res_coff=0, act=0, out=None, out_coff=0, in_coff=0, cin=None, mode=None, phase=None, weight_lp=None,
+         out_f16=False):
     """Launch cnb_conv2d.  `x` is (B, H, W, ldi); `weight` is the packed [cout][ntaps][cin] tensor.
     kind in {"1x1","3x3","3x3s2","4x4s2"} or phase=(py,px) for a ConvTranspose2d phase (then `out` is required
     and has spatial size (2H, 2W))."""
@@ -69,11 +70,12 @@ def conv(x, weight, kind, cout, *, bias=None, temb=None, temb_ld=0, temb_per_sam
         OHf, OWf = OH, OW
         oy_mul, oy_add, ox_mul, ox_add = 1, 0, 1, 0
     if out is None:
-        out = torch.empty((B, OHf, OWf, cout), device=x.device, dtype=torch.float32)
+        out = torch.empty((B, OHf, OWf, cout), device=x.device, dtype=torch.float16 if out_f16 else torch.float32)
     assert out.shape[0] == B and out.shape[1] == OHf and out.shape[2] == OWf, (out.shape, (B, OHf, OWf))
     p = rt.ConvParams()
     p.inp, p.weight, p.weight_lp = x.data_ptr(), weight.data_ptr(), rt.ptr(weight_lp)
     p.in_dtype = 1 if half else 0
+    p.out_dtype = 1 if out.dtype == torch.float16 else 0
     p.bias, p.temb, p.residual, p.out = rt.ptr(bias), rt.ptr(temb), rt.ptr(residual), out.data_ptr()
     p.B, p.H, p.W, p.Cin, p.ldi, p.in_coff = B, H, W, cin, ldi, in_coff
     p.OH, p.OW, p.OHf, p.OWf = OH, OW, OHf, OWf

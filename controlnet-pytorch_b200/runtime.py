@@ -30,7 +30,7 @@ class ConvParams(ctypes.Structure):
         ("stride", ctypes.c_int32), ("ntaps", ctypes.c_int32),
         ("dy", ctypes.c_int8 * MAX_TAPS), ("dx", ctypes.c_int8 * MAX_TAPS),
         ("temb_ld", ctypes.c_int32), ("temb_per_sample", ctypes.c_int32),
-        ("act", ctypes.c_int32), ("mode", ctypes.c_int32), ("in_dtype", ctypes.c_int32),
+        ("act", ctypes.c_int32), ("mode", ctypes.c_int32), ("in_dtype", ctypes.c_int32), ("out_dtype", ctypes.c_int32),
     ]
 
 

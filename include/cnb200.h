@@ -68,7 +68,7 @@ typedef struct cnb_conv_params {
   const float* bias;      /* [Cout] or NULL                                   */
   const float* temb;      /* [(B|1), temb_ld] or NULL                         */
   const float* residual;  /* [B, OHf, OWf, ldr] or NULL                       */
-  float* out;             /* [B, OHf, OWf, ldo]                               */
+  void* out;              /* [B, OHf, OWf, ldo] fp32 (out_dtype 0) or fp16 (out_dtype 1) */
   int32_t B, H, W, Cin, ldi, in_coff;
   int32_t OH, OW;         /* output grid that is iterated                     */
   int32_t OHf, OWf;       /* full spatial size of `out` / `residual`          */
@@ -83,6 +83,7 @@ typedef struct cnb_conv_params {
   int32_t act;            /* 0 = none, 1 = SiLU on the result                 */
   int32_t mode;           /* CNB_MODE_*                                       */
   int32_t in_dtype;       /* 0 = fp32 activations, 1 = fp16 activations (tensor-core modes only) */
+  int32_t out_dtype;      /* 0 = fp32 `out`, 1 = fp16 `out` (ldo / out_coff stay in elements; tensor-core modes only) */
 } cnb_conv_params;
 
 int cnb_conv2d(const cnb_conv_params* p, cnb_stream_t stream);

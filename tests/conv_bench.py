@@ -40,7 +40,12 @@ if what in ("conv", "all"):
               ("3x3", 64, 128, 14), ("3x3", 32, 64, 28), ("3x3", 16, 16, 28), ("3x3", 64, 16, 28),
               ("1x1", 64, 192, 28), ("1x1", 64, 64, 28), ("1x1", 256, 768, 7), ("1x1", 256, 256, 7),
               ("4x4s2", 64, 64, 28), ("3x3", 128, 32, 28)]
+    only = os.environ.get("CB_ONLY")
+    if only:
+        shapes = [shapes[int(i)] for i in only.split(",")]
     variants = [("f16", rt.MODE_TF32, True), ("tf32", rt.MODE_TF32, False)]
+    if os.environ.get("CB_VARIANT"):
+        variants = [v for v in variants if v[0] == os.environ["CB_VARIANT"]]
     if os.environ.get("CB_FP32", "0") == "1":
         variants.append(("fp32", rt.MODE_F32, False))
     for name, mode, half in variants:
@@ -56,7 +61,8 @@ if what in ("conv", "all"):
             bias = torch.randn(cout, device="cuda")
             oh = ops.out_size(kind, hw)
             out = torch.empty(B, oh, oh, cout, device="cuda")
-            ms = timeit(lambda: ops.conv(x, w, kind, cout, bias=bias, out=out, mode=mode, weight_lp=wl))
+            ms = timeit(lambda: ops.conv(x, w, kind, cout, bias=bias, out=out, mode=mode, weight_lp=wl,
+                                      act=int(os.environ.get('CB_ACT', '0'))))
             fl = 2.0 * B * oh * oh * k * cin * cout
             by = x.numel() * x.element_size() + 4.0 * out.numel() + w.numel() * (2 if half else 4)
             print(f"conv[{name}] {kind} {cin}->{cout} @{hw}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:8.1f} TFLOP/s  "

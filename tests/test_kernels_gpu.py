@@ -46,6 +46,9 @@ CONV_CASES = [
     ("3x3", 2, 16, 1, 28, 28), ("3x3", 1, 128, 32, 14, 14), ("3x3", 1, 256, 256, 7, 7), ("1x1", 2, 64, 64, 14, 14),
     ("1x1", 5, 32, 96, 7, 7), ("4x4s2", 2, 64, 64, 28, 28), ("4x4s2", 2, 128, 128, 14, 14), ("3x3s2", 2, 16, 32, 16, 16),
     ("3x3", 1, 36, 48, 5, 5), ("1x1", 1, 16, 48, 28, 28),
+    # TMA-im2col persistent kernel: several tiles per CTA, M tails, several N tiles, odd BN, strides
+    ("3x3", 32, 64, 64, 28, 28), ("3x3", 5, 64, 384, 9, 7), ("1x1", 40, 64, 192, 28, 28), ("3x3", 3, 128, 512, 7, 7),
+    ("3x3s2", 3, 64, 96, 16, 16), ("4x4s2", 33, 64, 48, 14, 14), ("3x3", 1, 32, 16, 3, 3), ("1x1", 1, 64, 16, 1, 1),
 ]
 
 
@@ -98,6 +101,10 @@ def test_conv_f16_operands(pk, kind, B, Cin, Cout, H, W):
     assert got.dtype == torch.float32
     assert rel_l2(nchw(got.cpu()), want_q) < 5e-6
     assert rel_l2(nchw(got.cpu()), want) < 1e-3
+    got16 = ops.conv(nhwc(x).cuda().half(), wp, kind, Cout, bias=b.cuda(), residual=nhwc(res).cuda(), mode=rt.MODE_TF32,
+                     weight_lp=ops.cast_f16(wp), out_f16=True)
+    assert got16.dtype == torch.float16
+    assert rel_l2(nchw(got16.float().cpu()), want_q) < 6e-4
     assert rt.lib().cnb_tc_error_flag() == 0
 
 
