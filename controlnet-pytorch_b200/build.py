@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libcnb200.so")
 STAMP = os.path.join(HERE, ".libcnb200.stamp")
-SOURCES = ["api.cu", "conv_f32.cu", "conv_tc.cu", "conv_tma.cu", "groupnorm.cu", "attention_f32.cu", "attention_tc.cu", "elementwise.cu"]
+SOURCES = ["api.cu", "conv_f32.cu", "conv_tc.cu", "conv_tma.cu", "groupnorm.cu", "attention_f32.cu", "attention_tc.cu", "attention_f16.cu", "elementwise.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-shared"]
 # --use_fast_math only affects the plain operators; every bit-exactness-critical expression in elementwise.cu
@@ -48,21 +48,27 @@ def build(force=False, verbose=False):
         with open(STAMP) as f:
             if f.read().strip() == dig:
                 return LIB
-    objs = []
     flags = [f for f in NVCC_FLAGS if f != "-shared"]
-    for src in SOURCES:
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+
+    def compile_one(src):
         obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        os.makedirs(os.path.dirname(obj), exist_ok=True)
         f = list(flags)
         if src == "elementwise.cu":
             f.remove("--use_fast_math")      # accurate sinf/cosf/logf/expf for the embedding + scheduler kernels
         cmd = [_nvcc()] + f + ["-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        if verbose or r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-        if r.returncode != 0:
-            raise RuntimeError("nvcc failed on " + src)
-        objs.append(obj)
+        return src, obj, r
+
+    from concurrent.futures import ThreadPoolExecutor
+    objs = []
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:   # one nvcc per source file
+        for src, obj, r in pool.map(compile_one, SOURCES):
+            if verbose or r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed on " + src)
+            objs.append(obj)
     cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

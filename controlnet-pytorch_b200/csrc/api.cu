@@ -30,6 +30,8 @@ int groupnorm(const float* x, void* y, const float* gamma, const float* beta, in
 int attention_f32(const float* qkv, float* out, int B, int L, int E, int heads, cudaStream_t st);
 int attention_tc(const float* qkv, float* out, int B, int L, int E, int heads, cudaStream_t st);
 bool attention_tc_supported(int E, int heads);
+int attention_f16(const void* qkv, void* out, int B, int L, int E, int heads, cudaStream_t st);
+bool attention_f16_supported(int E, int heads);
 
 static int g_has_tc = -1;
 static int query_tc() {
@@ -95,4 +97,13 @@ extern "C" int cnb_attention(const float* qkv, float* out, int B, int L, int E, 
   if (mode != CNB_MODE_F32 && attention_tc_supported(E, heads))
     return attention_tc(qkv, out, B, L, E, heads, (cudaStream_t)stream);
   return attention_f32(qkv, out, B, L, E, heads, (cudaStream_t)stream);   // exact fp32 core (and odd head dims)
+}
+
+extern "C" int cnb_attention_f16(const void* qkv, void* out, int B, int L, int E, int heads, cnb_stream_t stream) {
+  CNB_REQUIRE(qkv && out && B > 0 && L > 0 && E > 0, "attention_f16: bad args");
+  if (!attention_f16_supported(E, heads)) {
+    set_error("attention_f16: E=%d heads=%d (head dim %d) is not instantiated", E, heads, heads > 0 ? E / heads : 0);
+    return CNB_ERR_UNSUPPORTED;
+  }
+  return attention_f16(qkv, out, B, L, E, heads, (cudaStream_t)stream);
 }

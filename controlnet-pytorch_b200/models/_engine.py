@@ -67,6 +67,8 @@ def use_f16(mode, cin, cout):
 
 import os as _os
 _F16_ENABLED = _os.environ.get("CNB_F16", "1") != "0"
+ATTN_F16 = _os.environ.get("CNB_ATTN_F16", "1") != "0"
+ATTN_F16_DIMS = (4, 8, 16, 24, 32, 48, 64, 96, 128, 192)     # head dims attention_f16.cu instantiates
 
 
 def packed_convT(param, mode):
@@ -189,11 +191,14 @@ class ResAttnStack(nn.Module):
         E = att.embed_dim
         h16 = use_f16(mode, E, 3 * E)
         a = ops.groupnorm(x, raw(norm.weight), raw(norm.bias), self._groups, silu=False, out_f16=h16)
+        # tensor-core modes: q|k|v and the attention output stay fp16 between the three kernels
+        f16_core = h16 and ATTN_F16 and (E // att.num_heads) in ATTN_F16_DIMS
         qkv = ops.conv(a, packed_conv(att.in_proj_weight, mode), "1x1", 3 * E, bias=raw(att.in_proj_bias), mode=mode,
-                       weight_lp=packed_conv_f16(att.in_proj_weight, mode) if h16 else None)
+                       weight_lp=packed_conv_f16(att.in_proj_weight, mode) if h16 else None, out_f16=f16_core)
         o = ops.attention(qkv, att.num_heads, mode=mode)
         return ops.conv(o, packed_conv(att.out_proj.weight, mode), "1x1", E, bias=raw(att.out_proj.bias),
-                        residual=x, mode=mode)
+                        residual=x, mode=mode,
+                        weight_lp=packed_conv_f16(att.out_proj.weight, mode) if f16_core else None)
 
     def temb_channels(self):
         return [seq[1].out_features for seq in self.t_emb_layers] if self.t_emb_dim is not None else []

@@ -114,6 +114,10 @@ def attention(qkv, heads, mode=None):
     rt.require_cuda(qkv)
     B, H, W, E3 = qkv.shape
     E = E3 // 3
+    if qkv.dtype == torch.float16:
+        out = torch.empty((B, H, W, E), device=qkv.device, dtype=torch.float16)
+        rt.check(rt.lib().cnb_attention_f16(qkv.data_ptr(), out.data_ptr(), B, H * W, E, heads, rt.stream()))
+        return out
     out = torch.empty((B, H, W, E), device=qkv.device, dtype=torch.float32)
     rt.check(rt.lib().cnb_attention(qkv.data_ptr(), out.data_ptr(), B, H * W, E, heads,
                                     rt.get_mode() if mode is None else mode, rt.stream()))

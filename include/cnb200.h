@@ -113,6 +113,9 @@ int cnb_groupnorm(const float* x, void* y, const float* gamma, const float* beta
  * (unet_base.py:107; no mask, no dropout, attention weights discarded).
  */
 int cnb_attention(const float* qkv, float* out, int B, int L, int E, int heads, int mode, cnb_stream_t stream);
+/* Same contraction on fp16 operands: qkv [B, L, 3E] fp16 (as the in_proj convolution emits it with out_dtype 1),
+ * out [B, L, E] fp16 (the A operand of the out_proj convolution); fp32 softmax statistics and accumulators. */
+int cnb_attention_f16(const void* qkv, void* out, int B, int L, int E, int heads, cnb_stream_t stream);
 
 /* y[r, n] = post( sum_k pre(x[r, k]) * w[n, k] + b[n] ), pre/post = SiLU if the flag is set.  x is [R, K]
  * contiguous, y has leading dimension ldy.   Replaces Unet.t_proj (unet_base.py:313-317), the per-block

@@ -70,9 +70,14 @@ if what in ("conv", "all"):
 
 if what in ("attn", "all"):
     for mode in ((rt.MODE_TF32, rt.MODE_F32) if os.environ.get("CB_FP32", "0") == "1" else (rt.MODE_TF32,)):
-        for L, E, heads in [(784, 64, 4), (784, 16, 4), (196, 128, 4), (196, 32, 4), (49, 256, 4), (49, 128, 4), (49, 64, 4)]:
+        ashapes = [(784, 64, 4), (784, 16, 4), (196, 128, 4), (196, 32, 4), (49, 256, 4), (49, 128, 4), (49, 64, 4)]
+        if os.environ.get("CB_ONLY"):
+            ashapes = [ashapes[int(i)] for i in os.environ["CB_ONLY"].split(",")]
+        for L, E, heads in ashapes:
             side = int(math.isqrt(L))
             qkv = torch.randn(B, side, side, 3 * E, device="cuda")
+            if os.environ.get("CB_ATTN_F16", "1") == "1" and mode != rt.MODE_F32:
+                qkv = qkv.half()
             ms = timeit(lambda: ops.attention(qkv, heads, mode=mode))
             fl = 4.0 * B * L * L * E
             print(f"attn[{rt.mode_name(mode)}] L={L} E={E} d={E // heads}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:8.2f} TFLOP/s  "

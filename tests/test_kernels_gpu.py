@@ -157,6 +157,23 @@ def test_attention(pk, B, L, E, heads, mode, tol):
     assert rel_l2(got.cpu().reshape(B, L, E), want) < tol
 
 
+@pytest.mark.parametrize("B,L,E,heads", [(2, 784, 64, 4), (2, 784, 16, 4), (3, 196, 128, 4), (2, 49, 256, 4),
+                                         (2, 196, 32, 4), (1, 1024, 384, 16), (2, 64, 768, 16), (2, 16, 512, 16),
+                                         (1, 64, 512, 4), (1, 100, 384, 4), (1, 50, 768, 4), (2, 1, 64, 4), (1, 13, 32, 4),
+                                         (2, 1024, 128, 16), (3, 130, 64, 4)])
+def test_attention_f16(pk, B, L, E, heads):
+    """fp16-operand flash attention (mma.sync m16n8k16 + ldmatrix) against exact softmax attention on the same
+    fp16-rounded q|k|v; tolerance = fp16 rounding of P and of the output."""
+    ops, rt = pk
+    qkv = rnd(B, L, 3 * E, seed=1).half()
+    d = E // heads
+    q, k, v = [t.float().reshape(B, L, heads, d).transpose(1, 2) for t in qkv.split(E, dim=-1)]
+    want = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), -1) @ v).transpose(1, 2).reshape(B, L, E)
+    got = ops.attention(qkv.reshape(B, L, 1, 3 * E).cuda(), heads)
+    assert got.dtype == torch.float16
+    assert rel_l2(got.float().cpu().reshape(B, L, E), want) < 1.5e-3
+
+
 def test_time_embedding_and_linear(pk):
     ops, rt = pk
     import cn_oracle as O
