@@ -1,5 +1,6 @@
 // C-ABI glue: error text, launch counter, argument validation and mode dispatch.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -23,6 +24,8 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int conv2d_f32(const cnb_conv_params* p, cudaStream_t st);
 int conv2d_tc(const cnb_conv_params* p, cudaStream_t st);
 bool conv2d_tc_supported(const cnb_conv_params* p);
+int conv2d_small(const cnb_conv_params* p, cudaStream_t st);
+bool conv2d_small_supported(const cnb_conv_params* p);
 int conv2d_tma(const cnb_conv_params* p, cudaStream_t st);
 bool conv2d_tma_supported(const cnb_conv_params* p);
 int groupnorm(const float* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
@@ -72,6 +75,13 @@ extern "C" int cnb_conv2d(const cnb_conv_params* p, cnb_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   CNB_REQUIRE(p->in_dtype == 0 || p->in_dtype == 1, "conv2d: in_dtype=%d", p->in_dtype);
   CNB_REQUIRE(p->out_dtype == 0 || p->out_dtype == 1, "conv2d: out_dtype=%d", p->out_dtype);
+  static int small_on = -1;
+  if (small_on < 0) {
+    const char* e = getenv("CNB_CONV_SMALL");
+    small_on = e ? atoi(e) : 1;
+  }
+  // tiny-channel ends of the U-Net (Cin <= 4 or Cout <= 4): direct exact-fp32 kernels in every mode
+  if (small_on && (p->Cin <= 4 || p->Cout <= 4) && conv2d_small_supported(p)) return conv2d_small(p, st);
   if (p->mode == CNB_MODE_TF32 || p->mode == CNB_MODE_BF16) {
     if (conv2d_tma_supported(p)) return conv2d_tma(p, st);     // TMA-im2col fed persistent tcgen05 kernel
     if (conv2d_tc_supported(p)) return conv2d_tc(p, st);       // cp.async-gather tcgen05 kernel (narrow Cin)

@@ -46,7 +46,7 @@ def _cached(param, key, builder):
 
 def _tc_shape(o, i):
     """mirror of conv2d_tc_supported (csrc/conv_tc.cu): only layers that reach the tensor core get tf32 weights."""
-    return i % 4 == 0 and o % 16 == 0
+    return i % 4 == 0 and i > 4 and o % 16 == 0      # Cin <= 4 / Cout <= 4 layers run the exact direct kernels
 
 
 def packed_conv(param, mode):
@@ -306,8 +306,11 @@ def conv_in(unet, x_nhwc, mode, residual=None):
 
 
 def conv_out(unet, x, mode):
-    h = ops.groupnorm(x, raw(unet.norm_out.weight), raw(unet.norm_out.bias), unet.norm_out.num_groups, silu=True)
     co = unet.conv_out
+    # the direct small-Cout kernel reads fp16 activations in the tensor-core modes (half the bytes of this HBM-bound tail)
+    h16 = mode != rt.MODE_F32 and _F16_ENABLED and co.out_channels <= 4 and co.in_channels % 4 == 0
+    h = ops.groupnorm(x, raw(unet.norm_out.weight), raw(unet.norm_out.bias), unet.norm_out.num_groups, silu=True,
+                      out_f16=h16)
     return ops.conv(h, packed_conv(co.weight, mode), "3x3", co.out_channels, bias=raw(co.bias), mode=mode)
 
 

@@ -54,7 +54,7 @@ def conv(x, weight, kind, cout, *, bias=None, temb=None, temb_ld=0, temb_per_sam
     and has spatial size (2H, 2W))."""
     rt.require_cuda(x, weight, bias, temb, residual, out, weight_lp)
     half = x.dtype == torch.float16
-    if half and weight_lp is None:
+    if half and weight_lp is None and cout > 4:
         raise rt.CnbError("fp16 activations need the fp16 copy of the packed weights (weight_lp)")
     B, H, W, ldi = x.shape
     cin = ldi - in_coff if cin is None else cin

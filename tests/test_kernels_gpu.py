@@ -49,6 +49,9 @@ CONV_CASES = [
     # TMA-im2col persistent kernel: several tiles per CTA, M tails, several N tiles, odd BN, strides
     ("3x3", 32, 64, 64, 28, 28), ("3x3", 5, 64, 384, 9, 7), ("1x1", 40, 64, 192, 28, 28), ("3x3", 3, 128, 512, 7, 7),
     ("3x3s2", 3, 64, 96, 16, 16), ("4x4s2", 33, 64, 48, 14, 14), ("3x3", 1, 32, 16, 3, 3), ("1x1", 1, 64, 16, 1, 1),
+    # direct small-channel kernels: conv_in / hint conv0 / conv_out shapes of the three configs
+    ("3x3", 3, 4, 256, 8, 8), ("3x3", 2, 128, 4, 8, 8), ("3x3", 2, 16, 3, 9, 11), ("1x1", 2, 4, 4, 5, 5),
+    ("3x3", 2, 3, 16, 12, 12), ("4x4s2", 2, 3, 32, 8, 8),
 ]
 
 
@@ -172,6 +175,15 @@ def test_attention_f16(pk, B, L, E, heads):
     got = ops.attention(qkv.reshape(B, L, 1, 3 * E).cuda(), heads)
     assert got.dtype == torch.float16
     assert rel_l2(got.float().cpu().reshape(B, L, E), want) < 1.5e-3
+
+
+def test_conv_out_reads_fp16(pk):
+    """conv_out (Cout <= 4) on fp16 activations, as GroupNorm(norm_out) emits them in the tensor-core modes."""
+    ops, rt = pk
+    x, w, b = rnd(3, 16, 9, 7, seed=1), rnd(1, 16, 3, 3, seed=2) / 12.0, rnd(1, seed=3)
+    want = F.conv2d(x.half().float(), w, b, padding=1)
+    got = ops.conv(nhwc(x).cuda().half(), ops.pack_conv_weight(w.cuda(), False), "3x3", 1, bias=b.cuda(), mode=rt.MODE_TF32)
+    assert rel_l2(nchw(got.cpu()), want) < 2e-6
 
 
 def test_time_embedding_and_linear(pk):
