@@ -28,8 +28,8 @@ int conv2d_small(const cnb_conv_params* p, cudaStream_t st);
 bool conv2d_small_supported(const cnb_conv_params* p);
 int conv2d_tma(const cnb_conv_params* p, cudaStream_t st);
 bool conv2d_tma_supported(const cnb_conv_params* p);
-int groupnorm(const float* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
-              float eps, int silu, int out_f16, cudaStream_t st);
+int groupnorm(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
+              float eps, int silu, int in_f16, int out_f16, cudaStream_t st);
 int attention_f32(const float* qkv, float* out, int B, int L, int E, int heads, cudaStream_t st);
 int attention_tc(const float* qkv, float* out, int B, int L, int E, int heads, cudaStream_t st);
 bool attention_tc_supported(int E, int heads);
@@ -75,6 +75,7 @@ extern "C" int cnb_conv2d(const cnb_conv_params* p, cnb_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   CNB_REQUIRE(p->in_dtype == 0 || p->in_dtype == 1, "conv2d: in_dtype=%d", p->in_dtype);
   CNB_REQUIRE(p->out_dtype == 0 || p->out_dtype == 1, "conv2d: out_dtype=%d", p->out_dtype);
+  CNB_REQUIRE(p->res_dtype == 0 || p->res_dtype == 1, "conv2d: res_dtype=%d", p->res_dtype);
   static int small_on = -1;
   if (small_on < 0) {
     const char* e = getenv("CNB_CONV_SMALL");
@@ -90,15 +91,15 @@ extern "C" int cnb_conv2d(const cnb_conv_params* p, cnb_stream_t stream) {
     return CNB_ERR_BAD_ARG;
   }
   // fp32 mode, and tiny-channel layers (Cin % 4 != 0 or Cout < 16) which are HBM-bound CUDA-core work
-  CNB_REQUIRE(p->out_dtype == 0, "conv2d: fp16 output needs a tensor-core eligible layer");
+  CNB_REQUIRE(p->out_dtype == 0 && p->res_dtype == 0, "conv2d: fp16 output / residual needs a tensor-core eligible layer");
   CNB_REQUIRE(p->in_dtype == 0, "conv2d: fp16 activations need a tensor-core eligible layer (Cin %% 8 == 0, Cout %% 16 == 0)");
   return conv2d_f32(p, st);
 }
 
-extern "C" int cnb_groupnorm(const float* x, void* y, const float* gamma, const float* beta, int B, int HW, int C,
-                             int G, float eps, int silu, int out_f16, cnb_stream_t stream) {
+extern "C" int cnb_groupnorm(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C,
+                             int G, float eps, int silu, int in_f16, int out_f16, cnb_stream_t stream) {
   CNB_REQUIRE(x && y && gamma && beta && B > 0 && HW > 0 && C > 0 && G > 0, "groupnorm: bad args");
-  return groupnorm(x, y, gamma, beta, B, HW, C, G, eps, silu, out_f16, (cudaStream_t)stream);
+  return groupnorm(x, y, gamma, beta, B, HW, C, G, eps, silu, in_f16, out_f16, (cudaStream_t)stream);
 }
 
 extern "C" int cnb_attention(const float* qkv, float* out, int B, int L, int E, int heads, int mode,

@@ -210,7 +210,7 @@ conv_igemm_f32_kernel(const __grid_constant__ ConvArgs a) {
     int oy = r / p.OW, ox = r - (r / p.OW) * p.OW;
     long long pix = ((long long)b * p.OHf + (oy * p.oy_mul + p.oy_add)) * p.OWf + (ox * p.ox_mul + p.ox_add);
     float* dst = reinterpret_cast<float*>(p.out) + pix * p.ldo + p.out_coff;
-    const float* res = p.residual ? p.residual + pix * p.ldr + p.res_coff : nullptr;
+    const float* res = p.residual ? reinterpret_cast<const float*>(p.residual) + pix * p.ldr + p.res_coff : nullptr;
     const float* te = p.temb ? p.temb + (long long)(p.temb_per_sample ? b : 0) * p.temb_ld : nullptr;
 #pragma unroll
     for (int j = 0; j < TN; ++j) {

@@ -69,7 +69,17 @@ conv_small_cin_kernel(const __grid_constant__ SmallArgs a) {
       acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
     }
     if (p.residual) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(p.residual + pix * p.ldr + p.res_coff + n));
+      float4 t;
+      if (p.res_dtype == 1) {
+        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.residual) +
+                                                             pix * p.ldr + p.res_coff + n));
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+        t = make_float4(lo.x, lo.y, hi.x, hi.y);
+      } else {
+        t = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + pix * p.ldr +
+                                                  p.res_coff + n));
+      }
       acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
     }
     if (p.act == 1) { acc.x = silu_f(acc.x); acc.y = silu_f(acc.y); acc.z = silu_f(acc.z); acc.w = silu_f(acc.w); }
@@ -133,7 +143,9 @@ conv_small_cout_kernel(const __grid_constant__ SmallArgs a) {
     float v = acc[o];
     if (p.bias) v += __ldg(p.bias + o);
     if (p.temb) v += __ldg(p.temb + (size_t)(p.temb_per_sample ? b : 0) * p.temb_ld + o);
-    if (p.residual) v += __ldg(p.residual + pix * p.ldr + p.res_coff + o);
+    if (p.residual)
+      v += p.res_dtype == 1 ? __half2float(reinterpret_cast<const __half*>(p.residual)[pix * p.ldr + p.res_coff + o])
+                            : __ldg(reinterpret_cast<const float*>(p.residual) + pix * p.ldr + p.res_coff + o);
     if (p.act == 1) v = silu_f(v);
     reinterpret_cast<float*>(p.out)[pix * p.ldo + p.out_coff + o] = v;
   }

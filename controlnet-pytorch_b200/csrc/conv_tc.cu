@@ -226,7 +226,17 @@ conv_igemm_tc_kernel(const __grid_constant__ TcArgs a) {
             o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
           }
           if (p.residual) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(p.residual + pix * p.ldr + p.res_coff + n));
+            float4 t;
+            if (p.res_dtype == 1) {
+              const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.residual) +
+                                                                   pix * p.ldr + p.res_coff + n));
+              const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+              const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+              t = make_float4(lo.x, lo.y, hi.x, hi.y);
+            } else {
+              t = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + pix * p.ldr +
+                                                        p.res_coff + n));
+            }
             o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
           }
           if (p.act == 1) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }

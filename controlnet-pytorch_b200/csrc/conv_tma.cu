@@ -163,7 +163,7 @@ int conv2d_tma(const cnb_conv_params* p, cudaStream_t st) {
   a.OHf = p->OHf; a.OWf = p->OWf;
   a.oy_mul = p->oy_mul; a.oy_add = p->oy_add; a.ox_mul = p->ox_mul; a.ox_add = p->ox_add;
   a.Cout = p->Cout; a.ldo = p->ldo; a.out_coff = p->out_coff; a.ldr = p->ldr; a.res_coff = p->res_coff;
-  a.temb_ld = p->temb_ld; a.temb_per_sample = p->temb_per_sample; a.act = p->act; a.out_f16 = p->out_dtype == 1;
+  a.temb_ld = p->temb_ld; a.temb_per_sample = p->temb_per_sample; a.act = p->act; a.out_f16 = p->out_dtype == 1; a.res_f16 = p->res_dtype == 1;
   a.Cin = p->Cin; a.ntaps = p->ntaps; a.kchunks = p->Cin / kc;
   a.stride = p->stride; a.lower_w = dxmin; a.lower_h = dymin;
   a.tiles_m = ceil_div(a.M, BM); a.tiles_n = p->Cout / bn;

@@ -40,11 +40,11 @@ struct alignas(64) TmaArgs {
   CUtensorMap map_b;
   const float* bias;
   const float* temb;
-  const float* residual;
+  const void* residual;
   void* out;
   int M, OHW, OW;
   int OHf, OWf, oy_mul, oy_add, ox_mul, ox_add;
-  int Cout, ldo, out_coff, ldr, res_coff, temb_ld, temb_per_sample, act, out_f16;
+  int Cout, ldo, out_coff, ldr, res_coff, temb_ld, temb_per_sample, act, out_f16, res_f16;
   int Cin, ntaps, kchunks;
   int stride, lower_w, lower_h;
   int tiles_m, tiles_n;
@@ -76,6 +76,12 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
+}
+__device__ __forceinline__ float4 ld_half4(const __half* p) {
+  const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+  const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -120,7 +126,8 @@ struct Cfg {
                 "operand tiles must keep swizzle-atom alignment (8 rows x RB bytes)");
 };
 
-// EPI selects the epilogue: 0 = dense fp32 out, 1 = dense fp32 out + residual, 2 = dense fp16 out, 3 = generic.
+// EPI selects the epilogue: 0 = dense fp32 out, 1 = dense fp32 out + fp32 residual, 2 = dense fp16 out,
+// 4 = dense fp16 out + fp16 residual (the fp16 activation stream), 3 = generic.
 template <int BN, bool HALF, int EPI, int RB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tma_kernel(const __grid_constant__ TmaArgs a) {
@@ -299,18 +306,24 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
           const size_t o_off = (size_t)(m_w + sub_r) * ldo + a.out_coff + n;
           float4 rv[32 / RPI];
           if (EPI == 1) {
-            const float* rp = a.residual + (size_t)(m_w + sub_r) * ldr + a.res_coff + n;
+            const float* rp = reinterpret_cast<const float*>(a.residual) + (size_t)(m_w + sub_r) * ldr + a.res_coff + n;
 #pragma unroll
             for (int i = 0; i < 32 / RPI; ++i)
               if (i * RPI < rows_left) rv[i] = __ldg(reinterpret_cast<const float4*>(rp + (size_t)i * RPI * ldr));
+          }
+          if (EPI == 4) {
+            const __half* rp = reinterpret_cast<const __half*>(a.residual) + (size_t)(m_w + sub_r) * ldr + a.res_coff + n;
+#pragma unroll
+            for (int i = 0; i < 32 / RPI; ++i)
+              if (i * RPI < rows_left) rv[i] = ld_half4(rp + (size_t)i * RPI * ldr);
           }
 #pragma unroll
           for (int i = 0; i < 32 / RPI; ++i) {
             if (i * RPI < rows_left) {
               float4 o = *reinterpret_cast<const float4*>(sp + i * RPI * SSTR);
               o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-              if (EPI == 1) { o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w; }
-              if (EPI == 2) {
+              if (EPI == 1 || EPI == 4) { o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w; }
+              if (EPI == 2 || EPI == 4) {
                 const __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
                 *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(a.out) + o_off + (size_t)i * RPI * ldo) =
                     make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
@@ -334,7 +347,10 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
                 o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
               }
               if (a.residual) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(a.residual + rp * ldr + a.res_coff + n));
+                const float4 t = a.res_f16
+                    ? ld_half4(reinterpret_cast<const __half*>(a.residual) + rp * ldr + a.res_coff + n)
+                    : __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.residual) + rp * ldr +
+                                                            a.res_coff + n));
                 o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
               }
               if (a.act == 1) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
@@ -381,8 +397,9 @@ static int launch(const TmaArgs& a, int num_sms, cudaStream_t st) {
   const bool dense = a.oy_mul == 1 && a.ox_mul == 1 && a.oy_add == 0 && a.ox_add == 0 && a.OHf * a.OWf == a.OHW;
   const bool simple = dense && a.act == 0 && !(a.temb && a.temb_per_sample);
   if (simple && !a.out_f16 && !a.residual) return launch_epi<BN, HALF, 0, RB>(a, num_sms, st);
-  if (simple && !a.out_f16 && a.residual) return launch_epi<BN, HALF, 1, RB>(a, num_sms, st);
+  if (simple && !a.out_f16 && a.residual && !a.res_f16) return launch_epi<BN, HALF, 1, RB>(a, num_sms, st);
   if (simple && a.out_f16 && !a.residual) return launch_epi<BN, HALF, 2, RB>(a, num_sms, st);
+  if (simple && a.out_f16 && a.residual && a.res_f16) return launch_epi<BN, HALF, 4, RB>(a, num_sms, st);
   return launch_epi<BN, HALF, 3, RB>(a, num_sms, st);
 }
 

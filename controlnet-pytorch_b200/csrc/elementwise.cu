@@ -223,7 +223,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, float* __rest
   dst[bp * ldo + out_coff + c] = src[(b * C + c) * HW + pix];
 }
 
-__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, int ldi, int in_coff, float* __restrict__ dst,
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, int ldi, int in_coff, float* __restrict__ dst,
                                     int C, int HW, long long total) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // index over (b, c, p): p fastest
   if (i >= total) return;
@@ -231,10 +232,11 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, int ldi, int 
   long long bc = i / HW;
   int c = (int)(bc % C);
   long long b = bc / C;
-  dst[i] = src[(b * HW + pix) * ldi + in_coff + c];
+  dst[i] = (float)src[(b * HW + pix) * ldi + in_coff + c];
 }
 
-__global__ void copy_channels_kernel(const float* __restrict__ src, int lds, int s_coff, float* __restrict__ dst,
+template <typename T>
+__global__ void copy_channels_kernel(const T* __restrict__ src, int lds, int s_coff, T* __restrict__ dst,
                                      int ldd, int d_coff, int C, long long total) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -392,21 +394,36 @@ extern "C" int cnb_nchw_to_nhwc(const float* src, float* dst, int B, int C, int 
   return CNB_OK;
 }
 
-extern "C" int cnb_nhwc_to_nchw(const float* src, int ldi, int in_coff, float* dst, int B, int C, int HW,
+extern "C" int cnb_nhwc_to_nchw(const void* src, int ldi, int in_coff, float* dst, int B, int C, int HW, int src_f16,
                                 cnb_stream_t s) {
   long long total = (long long)B * C * HW;
   CNB_REQUIRE(total > 0 && ldi >= in_coff + C, "nhwc_to_nchw: bad dims");
-  nhwc_to_nchw_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)s>>>(src, ldi, in_coff, dst, C, HW, total);
+  if (src_f16)
+    nhwc_to_nchw_kernel<__half><<<blocks_for(total, 256), 256, 0, (cudaStream_t)s>>>(
+        reinterpret_cast<const __half*>(src), ldi, in_coff, dst, C, HW, total);
+  else
+    nhwc_to_nchw_kernel<float><<<blocks_for(total, 256), 256, 0, (cudaStream_t)s>>>(
+        reinterpret_cast<const float*>(src), ldi, in_coff, dst, C, HW, total);
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }
 
-extern "C" int cnb_copy_channels(const float* src, int lds, int s_coff, float* dst, int ldd, int d_coff,
-                                 long long npix, int C, cnb_stream_t s) {
+extern "C" int cnb_copy_channels(const void* src, int lds, int s_coff, void* dst, int ldd, int d_coff,
+                                 long long npix, int C, int elt, cnb_stream_t s) {
   long long total = npix * C;
-  CNB_REQUIRE(total > 0, "copy_channels: bad dims");
-  copy_channels_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)s>>>(src, lds, s_coff, dst, ldd, d_coff, C,
-                                                                           total);
+  CNB_REQUIRE(total > 0 && (elt == 4 || elt == 2), "copy_channels: bad dims");
+  if (elt == 2 && C % 2 == 0 && lds % 2 == 0 && s_coff % 2 == 0 && ldd % 2 == 0 && d_coff % 2 == 0) {
+    total /= 2;      // move fp16 pairs as 32-bit words
+    copy_channels_kernel<uint32_t><<<blocks_for(total, 256), 256, 0, (cudaStream_t)s>>>(
+        reinterpret_cast<const uint32_t*>(src), lds / 2, s_coff / 2, reinterpret_cast<uint32_t*>(dst), ldd / 2,
+        d_coff / 2, C / 2, total);
+  } else if (elt == 2) {
+    copy_channels_kernel<uint16_t><<<blocks_for(total, 256), 256, 0, (cudaStream_t)s>>>(
+        reinterpret_cast<const uint16_t*>(src), lds, s_coff, reinterpret_cast<uint16_t*>(dst), ldd, d_coff, C, total);
+  } else {
+    copy_channels_kernel<float><<<blocks_for(total, 256), 256, 0, (cudaStream_t)s>>>(
+        reinterpret_cast<const float*>(src), lds, s_coff, reinterpret_cast<float*>(dst), ldd, d_coff, C, total);
+  }
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }

@@ -25,9 +25,27 @@ template <> struct OutVec<true> {
   }
 };
 
-template <bool SILU, bool HALF>
+// input vector of 4 channels: float4 (fp32 stream) or 4 x fp16 (fp16 activation stream), widened to fp32
+template <bool HIN> struct InVec;
+template <> struct InVec<false> {
+  using type = float4;
+  static __device__ __forceinline__ float4 load(const float4* p) { return *p; }
+  static __device__ __forceinline__ float4 load_cs(const float4* p) { return __ldcs(p); }
+};
+template <> struct InVec<true> {
+  using type = uint2;
+  static __device__ __forceinline__ float4 widen(uint2 raw) {
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+  }
+  static __device__ __forceinline__ float4 load(const uint2* p) { return widen(*p); }
+  static __device__ __forceinline__ float4 load_cs(const uint2* p) { return widen(__ldcs(p)); }
+};
+
+template <bool SILU, bool HALF, bool HIN>
 __global__ void __launch_bounds__(1024)
-groupnorm_nhwc_kernel(const float* __restrict__ x, void* __restrict__ y, const float* __restrict__ gamma,
+groupnorm_nhwc_kernel(const void* __restrict__ x, void* __restrict__ y, const float* __restrict__ gamma,
                       const float* __restrict__ beta, int HW, int C, int G, float eps) {
   extern __shared__ float sm[];
   const int C4 = C >> 2;
@@ -42,7 +60,12 @@ groupnorm_nhwc_kernel(const float* __restrict__ x, void* __restrict__ y, const f
   const int col = tid % C4;
   const int r0 = tid / C4;
   const int cg = C / G;
-  const float4* xs = reinterpret_cast<const float4*>(x + (size_t)blockIdx.x * HW * C);
+  using IV = InVec<HIN>;
+  struct XS {   // xs[i] reads the i-th 4-channel vector of this sample as fp32
+    const typename IV::type* p;
+    __device__ __forceinline__ float4 operator[](size_t i) const { return IV::load(p + i); }
+  };
+  const XS xs{reinterpret_cast<const typename IV::type*>(x) + (size_t)blockIdx.x * HW * C4};
   using OV = OutVec<HALF>;
   typename OV::type* ys = reinterpret_cast<typename OV::type*>(y) + (size_t)blockIdx.x * HW * C4;
   const float inv_n = 1.0f / (float)(cg * HW);
@@ -168,9 +191,9 @@ __device__ __forceinline__ float ld_dsmem(const float* p, uint32_t cta_rank) {
   return v;
 }
 
-template <int KMAX, bool SILU, bool HALF>
+template <int KMAX, bool SILU, bool HALF, bool HIN>
 __global__ void __launch_bounds__(256)
-groupnorm_reg_kernel(const float* __restrict__ x, void* __restrict__ y, const float* __restrict__ gamma,
+groupnorm_reg_kernel(const void* __restrict__ x, void* __restrict__ y, const float* __restrict__ gamma,
                      const float* __restrict__ beta, int HW, int C, int G, float eps, int rows_per_cta) {
   extern __shared__ float sm[];
   const int C4 = C >> 2;
@@ -191,7 +214,8 @@ groupnorm_reg_kernel(const float* __restrict__ x, void* __restrict__ y, const fl
   const int row0 = rank * rows_per_cta;
   const int nrows = min(rows_per_cta, HW - row0);
   const size_t slab = ((size_t)blockIdx.y * HW + row0) * C4;
-  const float4* xs = reinterpret_cast<const float4*>(x) + slab;
+  using IV = InVec<HIN>;
+  const typename IV::type* xs = reinterpret_cast<const typename IV::type*>(x) + slab;
   using OV = OutVec<HALF>;
   typename OV::type* ys = reinterpret_cast<typename OV::type*>(y) + slab;
   const float inv_n = 1.0f / (float)(cg * HW);
@@ -200,7 +224,7 @@ groupnorm_reg_kernel(const float* __restrict__ x, void* __restrict__ y, const fl
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     const int row = r0 + k * R;
-    v[k] = row < nrows ? __ldcs(xs + (size_t)row * C4 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[k] = row < nrows ? IV::load_cs(xs + (size_t)row * C4 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 
   // ---- pass 1: sums -> group means
@@ -286,9 +310,17 @@ groupnorm_reg_kernel(const float* __restrict__ x, void* __restrict__ y, const fl
   if (split > 1) cluster_sync_all();
 }
 
+template <int KMAX, bool SILU, bool HALF, bool HIN>
+static cudaError_t launch_reg_one(cudaLaunchConfig_t* cfg, const void* x, void* y, const float* gamma, const float* beta,
+                                  int HW, int C, int G, float eps, int rows_per_cta) {
+  return cudaLaunchKernelEx(cfg, groupnorm_reg_kernel<KMAX, SILU, HALF, HIN>, x, y, gamma, beta, HW, C, G, eps,
+                            rows_per_cta);
+}
+
 template <int KMAX>
-static int launch_reg(const float* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
-                      float eps, int silu, int out_f16, int split, int rows_per_cta, int NT, cudaStream_t st) {
+static int launch_reg(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
+                      float eps, int silu, int in_f16, int out_f16, int split, int rows_per_cta, int NT,
+                      cudaStream_t st) {
   const int R = NT / (C / 4);
   const size_t smem = ((size_t)R * C + C + 4 * G) * sizeof(float);
   cudaLaunchConfig_t cfg;
@@ -305,14 +337,17 @@ static int launch_reg(const float* x, void* y, const float* gamma, const float* 
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e;
-  if (silu && out_f16)
-    e = cudaLaunchKernelEx(&cfg, groupnorm_reg_kernel<KMAX, true, true>, x, y, gamma, beta, HW, C, G, eps, rows_per_cta);
-  else if (silu)
-    e = cudaLaunchKernelEx(&cfg, groupnorm_reg_kernel<KMAX, true, false>, x, y, gamma, beta, HW, C, G, eps, rows_per_cta);
-  else if (out_f16)
-    e = cudaLaunchKernelEx(&cfg, groupnorm_reg_kernel<KMAX, false, true>, x, y, gamma, beta, HW, C, G, eps, rows_per_cta);
-  else
-    e = cudaLaunchKernelEx(&cfg, groupnorm_reg_kernel<KMAX, false, false>, x, y, gamma, beta, HW, C, G, eps, rows_per_cta);
+  const int sel = (silu ? 4 : 0) | (out_f16 ? 2 : 0) | (in_f16 ? 1 : 0);
+  switch (sel) {
+    case 0: e = launch_reg_one<KMAX, false, false, false>(&cfg, x, y, gamma, beta, HW, C, G, eps, rows_per_cta); break;
+    case 1: e = launch_reg_one<KMAX, false, false, true>(&cfg, x, y, gamma, beta, HW, C, G, eps, rows_per_cta); break;
+    case 2: e = launch_reg_one<KMAX, false, true, false>(&cfg, x, y, gamma, beta, HW, C, G, eps, rows_per_cta); break;
+    case 3: e = launch_reg_one<KMAX, false, true, true>(&cfg, x, y, gamma, beta, HW, C, G, eps, rows_per_cta); break;
+    case 4: e = launch_reg_one<KMAX, true, false, false>(&cfg, x, y, gamma, beta, HW, C, G, eps, rows_per_cta); break;
+    case 5: e = launch_reg_one<KMAX, true, false, true>(&cfg, x, y, gamma, beta, HW, C, G, eps, rows_per_cta); break;
+    case 6: e = launch_reg_one<KMAX, true, true, false>(&cfg, x, y, gamma, beta, HW, C, G, eps, rows_per_cta); break;
+    default: e = launch_reg_one<KMAX, true, true, true>(&cfg, x, y, gamma, beta, HW, C, G, eps, rows_per_cta); break;
+  }
   if (e != cudaSuccess) {
     set_error("groupnorm_reg launch failed: %s", cudaGetErrorString(e));
     return CNB_ERR_CUDA;
@@ -323,8 +358,14 @@ static int launch_reg(const float* x, void* y, const float* gamma, const float* 
 
 static int g_gn_reg = -1;
 
-int groupnorm(const float* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
-              float eps, int silu, int out_f16, cudaStream_t st) {
+template <bool SILU, bool HALF, bool HIN>
+static void launch_sweep(const void* x, void* y, const float* gamma, const float* beta, int B, int NT, size_t smem,
+                         int HW, int C, int G, float eps, cudaStream_t st) {
+  groupnorm_nhwc_kernel<SILU, HALF, HIN><<<B, NT, smem, st>>>(x, y, gamma, beta, HW, C, G, eps);
+}
+
+int groupnorm(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
+              float eps, int silu, int in_f16, int out_f16, cudaStream_t st) {
   CNB_REQUIRE(C % 4 == 0 && C % G == 0 && C / 4 <= 1024, "groupnorm: C=%d G=%d unsupported", C, G);
   if (g_gn_reg < 0) {
     const char* e = getenv("CNB_GN_REG");
@@ -346,10 +387,10 @@ int groupnorm(const float* x, void* y, const float* gamma, const float* beta, in
       const int rows = ceil_div(HW, split);
       const int k = ceil_div(rows, Rr);
       if (k <= 16) {
-        if (k <= 4) return launch_reg<4>(x, y, gamma, beta, B, HW, C, G, eps, silu, out_f16, split, rows, NTr, st);
-        if (k <= 8) return launch_reg<8>(x, y, gamma, beta, B, HW, C, G, eps, silu, out_f16, split, rows, NTr, st);
-        if (k <= 13) return launch_reg<13>(x, y, gamma, beta, B, HW, C, G, eps, silu, out_f16, split, rows, NTr, st);
-        return launch_reg<16>(x, y, gamma, beta, B, HW, C, G, eps, silu, out_f16, split, rows, NTr, st);
+        if (k <= 4) return launch_reg<4>(x, y, gamma, beta, B, HW, C, G, eps, silu, in_f16, out_f16, split, rows, NTr, st);
+        if (k <= 8) return launch_reg<8>(x, y, gamma, beta, B, HW, C, G, eps, silu, in_f16, out_f16, split, rows, NTr, st);
+        if (k <= 13) return launch_reg<13>(x, y, gamma, beta, B, HW, C, G, eps, silu, in_f16, out_f16, split, rows, NTr, st);
+        return launch_reg<16>(x, y, gamma, beta, B, HW, C, G, eps, silu, in_f16, out_f16, split, rows, NTr, st);
       }
     }
   }
@@ -360,14 +401,17 @@ int groupnorm(const float* x, void* y, const float* gamma, const float* beta, in
   const int NT = R * C4;
   size_t smem = ((size_t)R * C + C + 2 * G) * sizeof(float);
   CNB_REQUIRE(smem <= 48 * 1024, "groupnorm: smem %zu too large", smem);
-  if (silu && out_f16)
-    groupnorm_nhwc_kernel<true, true><<<B, NT, smem, st>>>(x, y, gamma, beta, HW, C, G, eps);
-  else if (silu)
-    groupnorm_nhwc_kernel<true, false><<<B, NT, smem, st>>>(x, y, gamma, beta, HW, C, G, eps);
-  else if (out_f16)
-    groupnorm_nhwc_kernel<false, true><<<B, NT, smem, st>>>(x, y, gamma, beta, HW, C, G, eps);
-  else
-    groupnorm_nhwc_kernel<false, false><<<B, NT, smem, st>>>(x, y, gamma, beta, HW, C, G, eps);
+  const int sel = (silu ? 4 : 0) | (out_f16 ? 2 : 0) | (in_f16 ? 1 : 0);
+  switch (sel) {
+    case 0: launch_sweep<false, false, false>(x, y, gamma, beta, B, NT, smem, HW, C, G, eps, st); break;
+    case 1: launch_sweep<false, false, true>(x, y, gamma, beta, B, NT, smem, HW, C, G, eps, st); break;
+    case 2: launch_sweep<false, true, false>(x, y, gamma, beta, B, NT, smem, HW, C, G, eps, st); break;
+    case 3: launch_sweep<false, true, true>(x, y, gamma, beta, B, NT, smem, HW, C, G, eps, st); break;
+    case 4: launch_sweep<true, false, false>(x, y, gamma, beta, B, NT, smem, HW, C, G, eps, st); break;
+    case 5: launch_sweep<true, false, true>(x, y, gamma, beta, B, NT, smem, HW, C, G, eps, st); break;
+    case 6: launch_sweep<true, true, false>(x, y, gamma, beta, B, NT, smem, HW, C, G, eps, st); break;
+    default: launch_sweep<true, true, true>(x, y, gamma, beta, B, NT, smem, HW, C, G, eps, st); break;
+  }
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }

@@ -43,9 +43,8 @@ def controlnet_forward(trained, control, down_zero, mid_zero, hint_feat_fn, x, t
     for i, d in enumerate(control.downs):
         B, H, W, C = c.shape
         zc = down_zero[i]
-        cat = ops.empty(B, H, W, 2 * C, device=dev)
-        ops.conv(c, E.packed_conv(zc.weight, mode), "1x1", C, bias=E.raw(zc.bias), residual=t_skips[i],
-                 out=cat, out_coff=C, mode=mode)
+        cat = ops.empty(B, H, W, 2 * C, device=dev, dtype=c.dtype)
+        E.conv16(c, zc.weight, "1x1", C, mode, bias=E.raw(zc.bias), residual=t_skips[i], out=cat, out_coff=C)
         cats.append(cat)
         c = E.run_down(d, c, plan_c[d], mode)
 
@@ -53,8 +52,7 @@ def controlnet_forward(trained, control, down_zero, mid_zero, hint_feat_fn, x, t
         c = E.run_mid(control.mids[i], c, plan_c[control.mids[i]], mode)
         a = E.run_mid(trained.mids[i], a, plan_t[trained.mids[i]], mode)
         zc = mid_zero[i]
-        a = ops.conv(c, E.packed_conv(zc.weight, mode), "1x1", zc.out_channels, bias=E.raw(zc.bias), residual=a,
-                     mode=mode)
+        a = E.conv16(c, zc.weight, "1x1", zc.out_channels, mode, bias=E.raw(zc.bias), residual=a)
 
     for u in trained.ups:
         a = E.run_up(u, a, None, plan_t[u], mode, cat=cats.pop())

@@ -68,7 +68,40 @@ def use_f16(mode, cin, cout):
 import os as _os
 _F16_ENABLED = _os.environ.get("CNB_F16", "1") != "0"
 ATTN_F16 = _os.environ.get("CNB_ATTN_F16", "1") != "0"
+_ACT16_ENABLED = _os.environ.get("CNB_ACT16", "1") != "0"
+
+
+def act16(mode):
+    """Tensor-core modes keep the whole activation stream (block inputs / outputs, skips, concat buffers) in fp16:
+    half the bytes of every HBM-bound kernel, every convolution runs kind::f16.  Statistics, accumulators, biases,
+    time-embedding rows and the softmax stay fp32.  CNB_ACT16=0 keeps the fp32 residual stream."""
+    return mode != rt.MODE_F32 and _F16_ENABLED and _ACT16_ENABLED
+
+
+def conv16(x, param, kind, cout, mode, *, packed=None, packed_lp=None, out_f16=None, **kw):
+    """ops.conv with the operand / output dtypes the mode implies: fp16 weights when x is fp16, fp16 output when the
+    activation stream is fp16 (unless the caller overrides out_f16)."""
+    w = packed_conv(param, mode) if packed is None else packed
+    lp = None
+    if x.dtype == torch.float16:
+        lp = packed_conv_f16(param, mode) if packed_lp is None else packed_lp
+    if out_f16 is None:
+        out_f16 = act16(mode) and cout % 16 == 0
+    return ops.conv(x, w, kind, cout, mode=mode, weight_lp=lp, out_f16=out_f16, **kw)
 ATTN_F16_DIMS = (4, 8, 16, 24, 32, 48, 64, 96, 128, 192)     # head dims attention_f16.cu instantiates
+
+
+def packed_convT_f16(param, mode):
+    return _cached(param, ("convT_f16",), lambda: ops.cast_f16(ops.pack_convT_weight(param, False)))
+
+
+def cast_like(x, ref):
+    """dtype bridge for the rare mixed case (a block called on its own with fp32 inputs while the stream is fp16)."""
+    if x.dtype == ref.dtype:
+        return x
+    if ref.dtype == torch.float16:
+        return ops.cast_f16(x)
+    raise rt.CnbError("cannot widen an fp16 activation into an fp32 buffer")
 
 
 def packed_convT(param, mode):
@@ -176,15 +209,13 @@ class ResAttnStack(nn.Module):
             trow, tld, tps = temb.row(self, j)
         else:
             trow, tld, tps = None, 0, False
-        h = ops.conv(h, packed_conv(first[2].weight, mode), "3x3", cout, bias=raw(first[2].bias),
-                     temb=trow, temb_ld=tld, temb_per_sample=tps, mode=mode,
-                     weight_lp=packed_conv_f16(first[2].weight, mode) if h16 else None)
+        h = conv16(h, first[2].weight, "3x3", cout, mode, bias=raw(first[2].bias),
+                   temb=trow, temb_ld=tld, temb_per_sample=tps)
         h16 = use_f16(mode, cout, cout)
         h = ops.groupnorm(h, raw(second[0].weight), raw(second[0].bias), self._groups, silu=True, out_f16=h16)
         rc = self.residual_input_conv[j]
-        r = ops.conv(x, packed_conv(rc.weight, mode), "1x1", cout, bias=raw(rc.bias), mode=mode)
-        return ops.conv(h, packed_conv(second[2].weight, mode), "3x3", cout, bias=raw(second[2].bias),
-                        residual=r, mode=mode, weight_lp=packed_conv_f16(second[2].weight, mode) if h16 else None)
+        r = conv16(x, rc.weight, "1x1", cout, mode, bias=raw(rc.bias))
+        return conv16(h, second[2].weight, "3x3", cout, mode, bias=raw(second[2].bias), residual=r)
 
     def _attention(self, j, x, mode):
         norm, att = self.attention_norms[j], self.attentions[j]
@@ -193,12 +224,9 @@ class ResAttnStack(nn.Module):
         a = ops.groupnorm(x, raw(norm.weight), raw(norm.bias), self._groups, silu=False, out_f16=h16)
         # tensor-core modes: q|k|v and the attention output stay fp16 between the three kernels
         f16_core = h16 and ATTN_F16 and (E // att.num_heads) in ATTN_F16_DIMS
-        qkv = ops.conv(a, packed_conv(att.in_proj_weight, mode), "1x1", 3 * E, bias=raw(att.in_proj_bias), mode=mode,
-                       weight_lp=packed_conv_f16(att.in_proj_weight, mode) if h16 else None, out_f16=f16_core)
+        qkv = conv16(a, att.in_proj_weight, "1x1", 3 * E, mode, bias=raw(att.in_proj_bias), out_f16=f16_core)
         o = ops.attention(qkv, att.num_heads, mode=mode)
-        return ops.conv(o, packed_conv(att.out_proj.weight, mode), "1x1", E, bias=raw(att.out_proj.bias),
-                        residual=x, mode=mode,
-                        weight_lp=packed_conv_f16(att.out_proj.weight, mode) if f16_core else None)
+        return conv16(o, att.out_proj.weight, "1x1", E, mode, bias=raw(att.out_proj.bias), residual=x)
 
     def temb_channels(self):
         return [seq[1].out_features for seq in self.t_emb_layers] if self.t_emb_dim is not None else []
@@ -211,7 +239,7 @@ def run_down(block, x, temb, mode):
             x = block._attention(j, x, mode)
     if block.down_sample:
         dc = block.down_sample_conv
-        x = ops.conv(x, packed_conv(dc.weight, mode), "4x4s2", dc.out_channels, bias=raw(dc.bias), mode=mode)
+        x = conv16(x, dc.weight, "4x4s2", dc.out_channels, mode, bias=raw(dc.bias))
     return x
 
 
@@ -235,17 +263,20 @@ def run_up(block, x, skip, temb, mode, cat=None):
     else:
         cu, OH, OW = C, H, W
     if cat is None:
+        dt = torch.float16 if (act16(mode) and (skip is None or skip.dtype == torch.float16)) else torch.float32
         if skip is None:
-            cat = ops.empty(B, OH, OW, cu, device=x.device)
+            cat = ops.empty(B, OH, OW, cu, device=x.device, dtype=dt)
         else:
-            cat = ops.empty(B, OH, OW, cu + skip.shape[3], device=x.device)
-            ops.copy_channels(skip, cat, d_coff=cu)
+            cat = ops.empty(B, OH, OW, cu + skip.shape[3], device=x.device, dtype=dt)
+            ops.copy_channels(cast_like(skip, cat), cat, d_coff=cu)
     if block.up_sample:
         wp = packed_convT(up.weight, mode)
+        wl = packed_convT_f16(up.weight, mode) if x.dtype == torch.float16 else None
         for ph in range(4):
-            ops.conv(x, wp[ph], None, cu, bias=raw(up.bias), out=cat, out_coff=0, mode=mode, phase=(ph >> 1, ph & 1))
+            ops.conv(x, wp[ph], None, cu, bias=raw(up.bias), out=cat, out_coff=0, mode=mode, phase=(ph >> 1, ph & 1),
+                     weight_lp=None if wl is None else wl[ph])
     else:
-        ops.copy_channels(x, cat, d_coff=0)
+        ops.copy_channels(cast_like(x, cat), cat, d_coff=0)
     x = cat
     for j in range(block.num_layers):
         x = block._resnet(j, x, temb, mode)
@@ -301,8 +332,7 @@ def unet_time(unet, t, device):
 
 def conv_in(unet, x_nhwc, mode, residual=None):
     ci = unet.conv_in
-    return ops.conv(x_nhwc, packed_conv(ci.weight, mode), "3x3", ci.out_channels, bias=raw(ci.bias),
-                    residual=residual, mode=mode)
+    return conv16(x_nhwc, ci.weight, "3x3", ci.out_channels, mode, bias=raw(ci.bias), residual=residual)
 
 
 def conv_out(unet, x, mode):
@@ -332,9 +362,9 @@ def hint_stack_ddpm(seq, hint_nhwc, mode):
     h = hint_nhwc
     for idx in (0, 2, 4):
         c = seq[idx]
-        h = ops.conv(h, packed_conv(c.weight, mode), "3x3", c.out_channels, bias=raw(c.bias), act=1, mode=mode)
+        h = conv16(h, c.weight, "3x3", c.out_channels, mode, bias=raw(c.bias), act=1)
     c = seq[6]
-    return ops.conv(h, packed_conv(c.weight, mode), "1x1", c.out_channels, bias=raw(c.bias), mode=mode)
+    return conv16(h, c.weight, "1x1", c.out_channels, mode, bias=raw(c.bias))
 
 
 class HintCache:

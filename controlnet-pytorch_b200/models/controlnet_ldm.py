@@ -65,8 +65,7 @@ class ControlNet(nn.Module):
         stages = list(self.control_unet_hint_block)
 
         def cv(conv, h, kind, act):
-            return ops.conv(h, E.packed_conv(conv.weight, mode), kind, conv.out_channels, bias=E.raw(conv.bias),
-                            act=act, mode=mode)
+            return E.conv16(h, conv.weight, kind, conv.out_channels, mode, bias=E.raw(conv.bias), act=act)
         h = cv(stages[0][0], hint_nhwc, "3x3", 1)
         for st in stages[1:-1]:
             h = cv(st[0], h, "3x3s2", 1)

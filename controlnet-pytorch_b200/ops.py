@@ -82,6 +82,7 @@ def conv(x, weight, kind, cout, *, bias=None, temb=None, temb_ld=0, temb_per_sam
     p.oy_mul, p.oy_add, p.ox_mul, p.ox_add = oy_mul, oy_add, ox_mul, ox_add
     p.Cout, p.ldo, p.out_coff = cout, out.shape[3], out_coff
     p.ldr, p.res_coff = (residual.shape[3] if residual is not None else 0), res_coff
+    p.res_dtype = 1 if (residual is not None and residual.dtype == torch.float16) else 0
     p.stride, p.ntaps = stride, len(taps)
     for i, (dy, dx) in enumerate(taps):
         p.dy[i], p.dx[i] = dy, dx
@@ -98,7 +99,8 @@ def groupnorm(x, gamma, beta, groups, silu, eps=1e-5, out_f16=False):
     B, H, W, C = x.shape
     y = torch.empty((B, H, W, C), device=x.device, dtype=torch.float16 if out_f16 else torch.float32)
     rt.check(rt.lib().cnb_groupnorm(x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, H * W, C,
-                                    groups, eps, 1 if silu else 0, 1 if out_f16 else 0, rt.stream()))
+                                    groups, eps, 1 if silu else 0, 1 if x.dtype == torch.float16 else 0,
+                                    1 if out_f16 else 0, rt.stream()))
     return y
 
 
@@ -160,10 +162,11 @@ def nhwc_to_nchw(x, in_coff=0, c=None):
     rt.require_cuda(x)
     B, H, W, ld = x.shape
     c = ld - in_coff if c is None else c
-    if c == 1 and ld == 1:
+    if c == 1 and ld == 1 and x.dtype == torch.float32:
         return x.reshape(B, 1, H, W)
     out = torch.empty((B, c, H, W), device=x.device, dtype=torch.float32)
-    rt.check(rt.lib().cnb_nhwc_to_nchw(x.data_ptr(), ld, in_coff, out.data_ptr(), B, c, H * W, rt.stream()))
+    rt.check(rt.lib().cnb_nhwc_to_nchw(x.data_ptr(), ld, in_coff, out.data_ptr(), B, c, H * W,
+                                       1 if x.dtype == torch.float16 else 0, rt.stream()))
     return out
 
 
@@ -171,8 +174,10 @@ def copy_channels(src, dst, d_coff, s_coff=0, c=None):
     rt.require_cuda(src, dst)
     B, H, W, lds = src.shape
     c = lds - s_coff if c is None else c
+    if src.dtype != dst.dtype:
+        raise rt.CnbError("copy_channels: source and destination must have the same dtype")
     rt.check(rt.lib().cnb_copy_channels(src.data_ptr(), lds, s_coff, dst.data_ptr(), dst.shape[3], d_coff, B * H * W,
-                                        c, rt.stream()))
+                                        c, src.element_size(), rt.stream()))
     return dst
 
 

@@ -30,7 +30,7 @@ class ConvParams(ctypes.Structure):
         ("stride", ctypes.c_int32), ("ntaps", ctypes.c_int32),
         ("dy", ctypes.c_int8 * MAX_TAPS), ("dx", ctypes.c_int8 * MAX_TAPS),
         ("temb_ld", ctypes.c_int32), ("temb_per_sample", ctypes.c_int32),
-        ("act", ctypes.c_int32), ("mode", ctypes.c_int32), ("in_dtype", ctypes.c_int32), ("out_dtype", ctypes.c_int32),
+        ("act", ctypes.c_int32), ("mode", ctypes.c_int32), ("in_dtype", ctypes.c_int32), ("out_dtype", ctypes.c_int32), ("res_dtype", ctypes.c_int32),
     ]
 
 
@@ -47,7 +47,7 @@ _SIGS = {
     "cnb_cast_bf16": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
     "cnb_cast_f16": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
     "cnb_groupnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int,
-                              c_int, c_void_p]),
+                              c_int, c_int, c_void_p]),
     "cnb_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "cnb_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "cnb_linear_small": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -62,8 +62,8 @@ _SIGS = {
     "cnb_edm_coeffs": (c_int, [c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cnb_scale_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_void_p]),
     "cnb_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "cnb_nhwc_to_nchw": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "cnb_copy_channels": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_ll, c_int, c_void_p]),
+    "cnb_nhwc_to_nchw": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "cnb_copy_channels": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_ll, c_int, c_int, c_void_p]),
     "cnb_tc_gemm_selftest": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "cnb_tc_error_flag": (c_int, []),
 }

@@ -67,7 +67,7 @@ typedef struct cnb_conv_params {
   const void* weight_lp;  /* fp16 copy of `weight`, required when in_dtype==1 */
   const float* bias;      /* [Cout] or NULL                                   */
   const float* temb;      /* [(B|1), temb_ld] or NULL                         */
-  const float* residual;  /* [B, OHf, OWf, ldr] or NULL                       */
+  const void* residual;   /* [B, OHf, OWf, ldr] fp32 (res_dtype 0) or fp16 (res_dtype 1), or NULL */
   void* out;              /* [B, OHf, OWf, ldo] fp32 (out_dtype 0) or fp16 (out_dtype 1) */
   int32_t B, H, W, Cin, ldi, in_coff;
   int32_t OH, OW;         /* output grid that is iterated                     */
@@ -84,6 +84,7 @@ typedef struct cnb_conv_params {
   int32_t mode;           /* CNB_MODE_*                                       */
   int32_t in_dtype;       /* 0 = fp32 activations, 1 = fp16 activations (tensor-core modes only) */
   int32_t out_dtype;      /* 0 = fp32 `out`, 1 = fp16 `out` (ldo / out_coff stay in elements; tensor-core modes only) */
+  int32_t res_dtype;      /* 0 = fp32 `residual`, 1 = fp16 `residual` (ldr / res_coff in elements)                   */
 } cnb_conv_params;
 
 int cnb_conv2d(const cnb_conv_params* p, cnb_stream_t stream);
@@ -99,13 +100,14 @@ int cnb_cast_bf16(const float* src, void* dst, long long n, cnb_stream_t stream)
 int cnb_cast_f16(const float* src, void* dst, long long n, cnb_stream_t stream);
 
 /*
- * GroupNorm (+ optional SiLU) over channels-last activations: x, y are [B, HW, C] contiguous; y is fp32, or fp16
- * when out_f16 != 0 (the operand type of the kind::f16 tensor-core convolution that consumes it).
+ * GroupNorm (+ optional SiLU) over channels-last activations: x, y are [B, HW, C] contiguous; x is fp32, or fp16
+ * when in_f16 != 0 (the fp16 activation stream of the tensor-core modes); y is fp32, or fp16 when out_f16 != 0 (the
+ * operand type of the kind::f16 tensor-core convolution that consumes it).  Statistics are always fp32.
  * Replaces nn.GroupNorm(G, C) [+ nn.SiLU] (unet_base.py:47-48,65-66,74,104-105,338 + :372; eps = 1e-5,
  * biased variance, per-channel affine).
  */
-int cnb_groupnorm(const float* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
-                  float eps, int silu, int out_f16, cnb_stream_t stream);
+int cnb_groupnorm(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
+                  float eps, int silu, int in_f16, int out_f16, cnb_stream_t stream);
 
 /*
  * Self-attention core on packed projections: qkv is [B, L, 3E] (q | k | v, heads split along E), out is [B, L, E].
@@ -164,9 +166,12 @@ int cnb_scale_rows(const float* a, const float* x, const float* c, const float* 
 
 /* layout plumbing between the reference's NCHW tensors and the channels-last workspace */
 int cnb_nchw_to_nhwc(const float* src, float* dst, int B, int C, int HW, int ldo, int out_coff, cnb_stream_t stream);
-int cnb_nhwc_to_nchw(const float* src, int ldi, int in_coff, float* dst, int B, int C, int HW, cnb_stream_t stream);
-int cnb_copy_channels(const float* src, int lds, int s_coff, float* dst, int ldd, int d_coff, long long npix,
-                      int C, cnb_stream_t stream);
+/* src is fp32 (src_f16 == 0) or fp16; dst is always the fp32 NCHW tensor of the public API */
+int cnb_nhwc_to_nchw(const void* src, int ldi, int in_coff, float* dst, int B, int C, int HW, int src_f16,
+                     cnb_stream_t stream);
+/* elt = bytes per element (4 or 2); offsets and leading dimensions in elements */
+int cnb_copy_channels(const void* src, int lds, int s_coff, void* dst, int ldd, int d_coff, long long npix,
+                      int C, int elt, cnb_stream_t stream);
 
 /* Self-test of the tcgen05 GEMM pipeline on an M x N x K problem (A [M,K], W [N,K], out [M,N], all fp32 device
  * buffers); returns CNB_ERR_TIMEOUT if an mbarrier wait exceeded its guard instead of hanging. */
