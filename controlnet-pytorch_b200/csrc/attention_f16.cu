@@ -5,7 +5,8 @@
 // be <10 % busy even at the MUFU limit of 148 SM x 16 x 1.9 GHz = 4.5 T scores/s.  The kernel is therefore built
 // to keep the MUFU pipe fed, not the tensor pipe: register-resident S/P (FA2 formulation), no TMEM round trip.
 //   * CTA = (batch, head) x BQ queries, one warp per 16 query rows; K/V tiles of BK keys are double-buffered in
-//     shared memory with cp.async (8- or 16-byte chunks; padded rows -> conflict-free ldmatrix);
+//     shared memory with cp.async (8- or 16-byte chunks; padded rows -> conflict-free ldmatrix), 3-stage ring with
+//     one block barrier per tile;
 //   * S = Q K^T and O += P V use mma.sync.m16n8k16 f16 with fp32 accumulate; K fragments come from ldmatrix.x4,
 //     V fragments from ldmatrix.x4.trans; the S accumulator fragment is re-packed in registers (cvt.rn.f16x2) as
 //     the A operand of the second MMA;
@@ -81,7 +82,7 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
   constexpr int KS = DP / 16;                    // k-steps of Q K^T
   constexpr int THREADS = NW * 32;
   static_assert(BK % 16 == 0, "BK must be a multiple of 16");
-  extern __shared__ __align__(16) __half smem[];   // [2 stages][K | V][BK][STRIDE]
+  extern __shared__ __align__(16) __half smem[];   // [3 stages][K | V][BK][STRIDE]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -94,7 +95,7 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
 
   // zero the pad columns once (cp.async only ever writes the d real columns)
   if (d < DP) {
-    for (int i = tid; i < 4 * TILE / 2; i += THREADS) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+    for (int i = tid; i < 6 * TILE / 2; i += THREADS) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
     __syncthreads();
   }
 
@@ -158,7 +159,7 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
   // one key tile; MASK = the (only) tile that may contain keys >= L
   auto tile_body = [&](int t, auto mask_tag) {
     constexpr bool MASK = decltype(mask_tag)::value;
-    const int stage = t & 1;
+    const int stage = t % 3;
     const uint32_t sK = smem_u + (uint32_t)(stage * 2 * TILE) * 2u;
     const uint32_t sV = sK + (uint32_t)TILE * 2u;
 
@@ -238,19 +239,18 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
     }
   };
 
+  // 3-stage ring, ONE block barrier per tile: the barrier that publishes tile t also proves every warp has finished
+  // tile t-1, whose stage is exactly the one tile t+2 is loaded into right after it.
   load_tile(0, 0);
+  if (ntiles > 1) load_tile(1, 1);
   const bool ragged = (L % BK) != 0;
   for (int t = 0; t < ntiles; ++t) {
-    if (t + 1 < ntiles) {
-      load_tile(t + 1, (t & 1) ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
+    if (t + 1 < ntiles) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    if (t + 2 < ntiles) load_tile(t + 2, (t + 2) % 3);
     if (ragged && t == ntiles - 1) tile_body(t, std::true_type{});
     else tile_body(t, std::false_type{});
-    __syncthreads();   // all warps done with this stage before it is refilled
   }
 
   // ---- normalise and store
@@ -272,7 +272,7 @@ static int g_h2 = -1;   // CNB_ATTN_EXP2H=1: ex2.approx.f16x2 exponentials (no f
 template <int D, int BK, int NW, bool H2>
 static int launch2(const void* qkv, void* out, int B, int L, int E, int heads, cudaStream_t st) {
   constexpr int DP = (D + 15) / 16 * 16;
-  constexpr size_t SMEM = (size_t)2 * 2 * BK * (DP + 8) * sizeof(__half);
+  constexpr size_t SMEM = (size_t)3 * 2 * BK * (DP + 8) * sizeof(__half);
   static bool attr_set = false;
   if (!attr_set) {
     CNB_CUDA(cudaFuncSetAttribute(attention_f16_kernel<D, BK, NW, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
