@@ -255,10 +255,17 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     rt.lib()
     rt.set_mode(args.mode)
+    eng = importlib.import_module("controlnet-pytorch_b200.models._engine")
+    # arithmetic type of the tensor-core mode: fp16 operands (fp32 accumulate) once GroupNorm / the activation stream emit fp16
+    dtype_name = "f32" if args.mode == "fp32" else ("f16" if eng._F16_ENABLED else "tf32")
     B = args.batch
     cfg, model, sched, hint_host = build_problem(B, dev, seed_offset=rank)
     per = 28 * 28
@@ -350,7 +357,7 @@ def run_b200(args):
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": dtype_name, "data": "synthetic",
                 "config": {"workload": "mnist_ddpm_controlnet_1000step", "batch_per_gpu": B, "global_batch": world * B,
                            "timesteps_per_sample": STEPS_PER_SAMPLE,
                            "step": "one denoising timestep: ControlNet eps + fused sample_prev_timestep (CUDA graph replay)",
@@ -362,9 +369,12 @@ def run_b200(args):
                 "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": int(smp.launches_per_step),
                 "roofline": roofline, "kernel_families": fam, "cpu_baseline": cpu_baseline,
                 "clocks": clk.summary(w0, w1)}
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
 
 
 def main():

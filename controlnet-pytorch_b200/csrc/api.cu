@@ -81,6 +81,12 @@ extern "C" int cnb_conv2d(const cnb_conv_params* p, cnb_stream_t stream) {
     const char* e = getenv("CNB_CONV_SMALL");
     small_on = e ? atoi(e) : 1;
   }
+  if (p->in2) {
+    CNB_REQUIRE(p->Cin2 > 0 && p->ldi2 >= p->in2_coff + p->Cin2, "conv2d: bad second input");
+    CNB_REQUIRE(p->mode != CNB_MODE_F32 && conv2d_tma_supported(p),
+                "conv2d: a second input (K-concatenated 1x1 tap) needs the TMA tensor-core path");
+    return conv2d_tma(p, st);
+  }
   // tiny-channel ends of the U-Net (Cin <= 4 or Cout <= 4): direct exact-fp32 kernels in every mode
   if (small_on && (p->Cin <= 4 || p->Cout <= 4) && conv2d_small_supported(p)) return conv2d_small(p, st);
   if (p->mode == CNB_MODE_TF32 || p->mode == CNB_MODE_BF16) {

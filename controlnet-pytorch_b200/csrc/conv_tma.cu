@@ -76,6 +76,11 @@ bool conv2d_tma_supported(const cnb_conv_params* p) {
   const int elt = half ? 2 : 4;
   if (half && !p->weight_lp) return false;
   if (pick_rb(p->Cin, elt) == 0) return false;
+  if (p->in2) {
+    if (p->stride != 1 || p->H != p->OH || p->W != p->OW) return false;      // second input lives on the output grid
+    if (p->Cin2 % (16 / elt)) return false;      // rows of the second input must be whole 16-byte chunks
+    if ((p->ldi2 * elt) % 16 || (p->in2_coff * elt) % 16 || ((uintptr_t)p->in2 & 15)) return false;
+  }
   if ((p->ldi * elt) % 16 || (p->in_coff * elt) % 16) return false;
   if (pick_bn(p->Cout) == 0) return false;
   const int oelt = p->out_dtype == 1 ? 2 : 4;
@@ -105,6 +110,8 @@ int conv2d_tma(const cnb_conv_params* p, cudaStream_t st) {
   if (rc != CNB_OK) return rc;
   const bool half = p->in_dtype == 1;
   const int elt = half ? 2 : 4;
+  // the second input reuses the main input's chunk width; a last partial chunk is zero-filled by TMA (channels and
+  // weight columns past the end are out of bounds)
   const int rb = pick_rb(p->Cin, elt), kc = rb / elt;
   const CUtensorMapSwizzle swz = rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                            : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -140,10 +147,31 @@ int conv2d_tma(const cnb_conv_params* p, cudaStream_t st) {
     const size_t bytes = (size_t)p->B * p->H * p->W * p->ldi * elt;
     if (g_driver_version <= 13010 && bytes < 131072) reinterpret_cast<uint64_t*>(&a.map_a)[1] &= ~(1llu << 21);
   }
+  // ---- optional second input: [B, OH, OW, ldi2], a single (0,0) tap on the output grid
+  if (p->in2) {
+    const int zero2[2] = {0, 0};
+    const cuuint64_t dims[4] = {(cuuint64_t)p->Cin2, (cuuint64_t)p->OW, (cuuint64_t)p->OH, (cuuint64_t)p->B};
+    const cuuint64_t strides[3] = {(cuuint64_t)p->ldi2 * elt, (cuuint64_t)p->OW * p->ldi2 * elt,
+                                   (cuuint64_t)p->OH * p->OW * p->ldi2 * elt};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    void* base = const_cast<char*>(reinterpret_cast<const char*>(p->in2) + (size_t)p->in2_coff * elt);
+    CUresult r = g_encode_im2col(&a.map_a2, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                                 base, dims, strides, zero2, zero2, (cuuint32_t)kc, (cuuint32_t)BM, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeIm2col(second input) failed (%d): Cin2=%d OW=%d OH=%d B=%d ldi2=%d", (int)r, p->Cin2,
+                p->OW, p->OH, p->B, p->ldi2);
+      return CNB_ERR_CUDA;
+    }
+    const size_t bytes2 = (size_t)p->B * p->OH * p->OW * p->ldi2 * elt;
+    if (g_driver_version <= 13010 && bytes2 < 131072) reinterpret_cast<uint64_t*>(&a.map_a2)[1] &= ~(1llu << 21);
+    a.kchunks2 = ceil_div(p->Cin2, kc);
+  }
   // ---- packed weights [Cout][K] -> tile {kc, BN}
   const int bn = pick_bn(p->Cout);
   {
-    const int K = p->ntaps * p->Cin;
+    const int K = p->ntaps * p->Cin + (p->in2 ? p->Cin2 : 0);
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)p->Cout};
     const cuuint64_t strides[1] = {(cuuint64_t)K * elt};
     const cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)bn};

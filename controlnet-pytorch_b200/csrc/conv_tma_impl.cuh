@@ -37,6 +37,7 @@ constexpr int SMEM_BUDGET = 227 * 1024;
 
 struct alignas(64) TmaArgs {
   CUtensorMap map_a;
+  CUtensorMap map_a2;   // optional second input (one (0,0) tap appended to K); used when kchunks2 > 0
   CUtensorMap map_b;
   const float* bias;
   const float* temb;
@@ -45,7 +46,7 @@ struct alignas(64) TmaArgs {
   int M, OHW, OW;
   int OHf, OWf, oy_mul, oy_add, ox_mul, ox_add;
   int Cout, ldo, out_coff, ldr, res_coff, temb_ld, temb_per_sample, act, out_f16, res_f16;
-  int Cin, ntaps, kchunks;
+  int Cin, ntaps, kchunks, kchunks2;
   int stride, lower_w, lower_h;
   int tiles_m, tiles_n;
   uint32_t tap_off[CNB_MAX_TAPS];   // offset_w | offset_h << 16
@@ -155,7 +156,7 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const int nkb = a.ntaps * a.kchunks;
+  const int nkb = a.ntaps * a.kchunks + a.kchunks2;
   const int ntiles = a.tiles_m * a.tiles_n;
 
   if (tid == 0) {
@@ -201,6 +202,16 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
                                (uint16_t)(off >> 16));
             tma_load_2d(sa + A_STAGE_BYTES, &a.map_b, &full_bar[s], tap * a.Cin + kc * KC, nt * BN);
           }
+        }
+        // second input: one (0,0) tap over the output grid, weight columns after the ntaps*Cin of the main input
+        for (int kc = 0; kc < a.kchunks2 && ok; ++kc, ++it) {
+          const int s = it % S;
+          if (it >= S) ok = mbar_wait(&empty_bar[s], (uint32_t)(((it / S) - 1) & 1), abort_flag);
+          if (!ok) break;
+          const uint32_t sa = smem_base + (uint32_t)s * C::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], (uint32_t)C::STAGE_BYTES);
+          tma_load_im2col_4d(sa, &a.map_a2, &full_bar[s], kc * KC, ox, oy, b, (uint16_t)0, (uint16_t)0);
+          tma_load_2d(sa + A_STAGE_BYTES, &a.map_b, &full_bar[s], a.ntaps * a.Cin + kc * KC, nt * BN);
         }
         if (!ok) break;
       }

@@ -91,6 +91,33 @@ def conv16(x, param, kind, cout, mode, *, packed=None, packed_lp=None, out_f16=N
 ATTN_F16_DIMS = (4, 8, 16, 24, 32, 48, 64, 96, 128, 192)     # head dims attention_f16.cu instantiates
 
 
+_FUSE_RES = _os.environ.get("CNB_FUSE_RES", "1") != "0"
+
+
+def fuse_residual(mode, x, h, cout):
+    """K-concatenation needs both operands fp16 and TMA-friendly channel counts."""
+    if not (_FUSE_RES and act16(mode) and x.dtype == torch.float16 and h.dtype == torch.float16):
+        return False
+    return h.shape[3] % 16 == 0 and x.shape[3] % 8 == 0 and cout % 16 == 0
+
+
+def packed_cat_f16(param3x3, param1x1):
+    """fp16 [Cout][9*C + Cin] rows: the second 3x3's packed taps followed by the 1x1 residual conv's columns."""
+    def build():
+        a = ops.pack_conv_weight(param3x3, False)
+        b = ops.pack_conv_weight(param1x1, False)
+        o = a.shape[0]
+        return ops.cast_f16(torch.cat([a.reshape(o, -1), b.reshape(o, -1)], dim=1).contiguous())
+    store = param3x3.__dict__.setdefault("_cnb_pack", {})
+    stamp = (param3x3._version, param3x3.data_ptr(), param1x1._version, param1x1.data_ptr())
+    ent = store.get(("cat_f16",))
+    if ent is None or ent[0] != stamp:
+        with torch.no_grad():
+            ent = (stamp, build())
+        store[("cat_f16",)] = ent
+    return ent[1]
+
+
 def packed_convT_f16(param, mode):
     return _cached(param, ("convT_f16",), lambda: ops.cast_f16(ops.pack_convT_weight(param, False)))
 
@@ -214,6 +241,12 @@ class ResAttnStack(nn.Module):
         h16 = use_f16(mode, cout, cout)
         h = ops.groupnorm(h, raw(second[0].weight), raw(second[0].bias), self._groups, silu=True, out_f16=h16)
         rc = self.residual_input_conv[j]
+        if fuse_residual(mode, x, h, cout):
+            # "+ residual_input_conv(resnet_input)" (unet_base.py:100) as extra K of the second 3x3: one launch, no
+            # round trip of the 1x1 result through HBM; its bias rides in the epilogue's broadcast-row slot
+            w = packed_conv(second[2].weight, mode)
+            return ops.conv(h, w, "3x3", cout, bias=raw(second[2].bias), temb=raw(rc.bias), temb_ld=cout,
+                            mode=mode, weight_lp=packed_cat_f16(second[2].weight, rc.weight), out_f16=True, x2=x)
         r = conv16(x, rc.weight, "1x1", cout, mode, bias=raw(rc.bias))
         return conv16(h, second[2].weight, "3x3", cout, mode, bias=raw(second[2].bias), residual=r)
 

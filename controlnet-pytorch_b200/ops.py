@@ -48,11 +48,11 @@ def empty(*shape, device, dtype=torch.float32):
 
 def conv(x, weight, kind, cout, *, bias=None, temb=None, temb_ld=0, temb_per_sample=False, residual=None,
          res_coff=0, act=0, out=None, out_coff=0, in_coff=0, cin=None, mode=None, phase=None, weight_lp=None,
-         out_f16=False):
+         out_f16=False, x2=None, x2_coff=0, cin2=None):
     """Launch cnb_conv2d.  `x` is (B, H, W, ldi); `weight` is the packed [cout][ntaps][cin] tensor.
     kind in {"1x1","3x3","3x3s2","4x4s2"} or phase=(py,px) for a ConvTranspose2d phase (then `out` is required
     and has spatial size (2H, 2W))."""
-    rt.require_cuda(x, weight, bias, temb, residual, out, weight_lp)
+    rt.require_cuda(x, weight, bias, temb, residual, out, weight_lp, x2)
     half = x.dtype == torch.float16
     if half and weight_lp is None and cout > 4:
         raise rt.CnbError("fp16 activations need the fp16 copy of the packed weights (weight_lp)")
@@ -83,6 +83,11 @@ def conv(x, weight, kind, cout, *, bias=None, temb=None, temb_ld=0, temb_per_sam
     p.Cout, p.ldo, p.out_coff = cout, out.shape[3], out_coff
     p.ldr, p.res_coff = (residual.shape[3] if residual is not None else 0), res_coff
     p.res_dtype = 1 if (residual is not None and residual.dtype == torch.float16) else 0
+    if x2 is not None:      # second input on the output grid, one extra (0,0) tap appended to K (see cnb200.h)
+        if x2.dtype != x.dtype or tuple(x2.shape[:3]) != (B, OH, OW):
+            raise rt.CnbError("conv: second input must share the first input's dtype and the output grid")
+        p.in2, p.ldi2, p.in2_coff = x2.data_ptr(), x2.shape[3], x2_coff
+        p.Cin2 = (x2.shape[3] - x2_coff) if cin2 is None else cin2
     p.stride, p.ntaps = stride, len(taps)
     for i, (dy, dx) in enumerate(taps):
         p.dy[i], p.dx[i] = dy, dx

@@ -31,6 +31,7 @@ class ConvParams(ctypes.Structure):
         ("dy", ctypes.c_int8 * MAX_TAPS), ("dx", ctypes.c_int8 * MAX_TAPS),
         ("temb_ld", ctypes.c_int32), ("temb_per_sample", ctypes.c_int32),
         ("act", ctypes.c_int32), ("mode", ctypes.c_int32), ("in_dtype", ctypes.c_int32), ("out_dtype", ctypes.c_int32), ("res_dtype", ctypes.c_int32),
+        ("in2", c_void_p), ("Cin2", ctypes.c_int32), ("ldi2", ctypes.c_int32), ("in2_coff", ctypes.c_int32),
     ]
 
 

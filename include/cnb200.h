@@ -53,6 +53,7 @@ int cnb_has_tcgen05(void);
  * Implicit-GEMM convolution / linear layer with fused epilogue.
  *   out[b, oy*oy_mul+oy_add, ox*ox_mul+ox_add, out_coff+n] =
  *        act( sum_{tap,c} W[n][tap][c] * in[b, oy*stride+dy[tap], ox*stride+dx[tap], in_coff+c]   (0 outside)
+ *             [+ sum_c W[n][ntaps][c] * in2[b, oy, ox, in2_coff+c]]
  *             + bias[n] + temb[(temb_per_sample ? b : 0)*temb_ld + n] + residual[b, oy', ox', res_coff+n] )
  * Replaces nn.Conv2d 3x3/1x1/4x4s2/3x3s2 (models/unet_base.py:49,67,84,88,131,149,166,220,238,259,320,339;
  * models/blocks.py:54,73,112,...; models/controlnet.py:70-106; models/controlnet_ldm.py:48-96), one output-parity
@@ -85,6 +86,11 @@ typedef struct cnb_conv_params {
   int32_t in_dtype;       /* 0 = fp32 activations, 1 = fp16 activations (tensor-core modes only) */
   int32_t out_dtype;      /* 0 = fp32 `out`, 1 = fp16 `out` (ldo / out_coff stay in elements; tensor-core modes only) */
   int32_t res_dtype;      /* 0 = fp32 `residual`, 1 = fp16 `residual` (ldr / res_coff in elements)                   */
+  /* Optional second input, contracted with one extra (0,0) tap: [B, OH, OW, ldi2] of `in`'s dtype; the packed weight
+   * rows are then [ntaps*Cin | Cin2] long.  This is how "+ residual_input_conv(resnet_input)" (unet_base.py:100) is
+   * folded into the second 3x3 convolution of a resnet block as extra K.  NULL when unused; tcgen05 path only. */
+  const void* in2;
+  int32_t Cin2, ldi2, in2_coff;
 } cnb_conv_params;
 
 int cnb_conv2d(const cnb_conv_params* p, cnb_stream_t stream);

@@ -177,6 +177,25 @@ def test_attention_f16(pk, B, L, E, heads):
     assert rel_l2(got.float().cpu().reshape(B, L, E), want) < 1.5e-3
 
 
+@pytest.mark.parametrize("B,C,Cx,Cout,H,W", [(3, 64, 64, 64, 14, 14), (2, 64, 32, 64, 28, 28), (5, 128, 256, 128, 7, 7),
+                                             (2, 16, 64, 16, 9, 11), (33, 32, 32, 32, 14, 14)])
+def test_conv_k_concat_second_input(pk, B, C, Cx, Cout, H, W):
+    """3x3 conv over h plus a 1x1 conv over a second input x folded in as extra K (resnet residual_input_conv)."""
+    ops, rt = pk
+    h, x = rnd(B, C, H, W, seed=1), rnd(B, Cx, H, W, seed=2)
+    w3, w1 = rnd(Cout, C, 3, 3, seed=3) / math.sqrt(9 * C), rnd(Cout, Cx, 1, 1, seed=4) / math.sqrt(Cx)
+    b3, b1 = rnd(Cout, seed=5), rnd(Cout, seed=6)
+    want = (F.conv2d(h.half().float(), w3.half().float(), b3, padding=1) +
+            F.conv2d(x.half().float(), w1.half().float(), b1))
+    p3, p1 = ops.pack_conv_weight(w3.cuda(), False), ops.pack_conv_weight(w1.cuda(), False)
+    wcat = ops.cast_f16(torch.cat([p3.reshape(Cout, -1), p1.reshape(Cout, -1)], dim=1).contiguous())
+    got = ops.conv(nhwc(h).cuda().half(), p3, "3x3", Cout, bias=b3.cuda(), temb=b1.cuda(), temb_ld=Cout,
+                   mode=rt.MODE_TF32, weight_lp=wcat, out_f16=True, x2=nhwc(x).cuda().half())
+    assert got.dtype == torch.float16
+    assert rel_l2(nchw(got.float().cpu()), want) < 6e-4
+    assert rt.lib().cnb_tc_error_flag() == 0
+
+
 def test_conv_out_reads_fp16(pk):
     """conv_out (Cout <= 4) on fp16 activations, as GroupNorm(norm_out) emits them in the tensor-core modes."""
     ops, rt = pk
