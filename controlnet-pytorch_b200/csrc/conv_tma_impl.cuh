@@ -49,6 +49,10 @@ struct alignas(64) TmaArgs {
   int Cin, ntaps, kchunks, kchunks2;
   int stride, lower_w, lower_h;
   int tiles_m, tiles_n;
+  // shared-memory plan (runtime: the resident-weights variant trades ring depth for a [nkb][BN x RB] weight area)
+  int bres;         // 1 = the whole packed weight tile stays resident in smem, the ring carries A stages only
+  int s_run;        // ring depth actually used (<= Cfg::S)
+  int ring_off, stage_bytes, epi_off, bar_off;
   uint32_t tap_off[CNB_MAX_TAPS];   // offset_w | offset_h << 16
 };
 
@@ -146,11 +150,16 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
   uint8_t* smem = smem_raw + pad;
   const uint32_t smem_base = raw_addr + pad;
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::BAR_OFFSET);   // [S]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + a.bar_off);       // [S]
   uint64_t* empty_bar = full_bar + S;                                       // [S]
   uint64_t* tfull_bar = empty_bar + S;                                      // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;                                     // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* bres_bar = tempty_bar + 2;                                      // [1] resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
+  const int s_run = a.s_run;
+  const uint32_t ring_base = smem_base + (uint32_t)a.ring_off;
+  const uint32_t stage_bytes = (uint32_t)a.stage_bytes;
+  const bool bres = a.bres != 0;
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int tid = threadIdx.x;
@@ -168,6 +177,7 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], EPI_WARPS);
     }
+    mbar_init(bres_bar, 1);
     *abort_flag = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -180,8 +190,28 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
-      int it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      if (bres) {
+        // resident weights: every k-block's {chunk, BN} tile once per CTA (tiles_n == 1)
+        mbar_expect_tx(bres_bar, (uint32_t)(nkb * C::B_STAGE_BYTES));
+        int kb = 0;
+        for (int tap = 0; tap < a.ntaps; ++tap)
+          for (int kc = 0; kc < a.kchunks; ++kc, ++kb)
+            tma_load_2d(smem_base + (uint32_t)(kb * C::B_STAGE_BYTES), &a.map_b, bres_bar, tap * a.Cin + kc * KC, 0);
+        for (int kc = 0; kc < a.kchunks2; ++kc, ++kb)
+          tma_load_2d(smem_base + (uint32_t)(kb * C::B_STAGE_BYTES), &a.map_b, bres_bar, a.ntaps * a.Cin + kc * KC, 0);
+      }
+      const uint32_t tx = bres ? (uint32_t)A_STAGE_BYTES : (uint32_t)C::STAGE_BYTES;
+      int s = 0, round = 0;
+      bool ok = true;
+      auto stage_begin = [&]() -> uint32_t {      // waits for the slot, arms its barrier, returns its smem address
+        if (round > 0) ok = mbar_wait(&empty_bar[s], (uint32_t)((round - 1) & 1), abort_flag);
+        if (ok) mbar_expect_tx(&full_bar[s], tx);
+        return ring_base + (uint32_t)s * stage_bytes;
+      };
+      auto stage_end = [&]() {
+        if (++s == s_run) { s = 0; ++round; }
+      };
+      for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
         const int mt = tile / a.tiles_n, nt = tile - mt * a.tiles_n;
         const int m0 = mt * BM;
         const int b = m0 / a.OHW;
@@ -189,50 +219,45 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
         const int oy = rem / a.OW;
         const int ox = rem - oy * a.OW;
         const int w0 = ox * a.stride + a.lower_w, h0 = oy * a.stride + a.lower_h;
-        bool ok = true;
         for (int tap = 0; tap < a.ntaps && ok; ++tap) {
           const uint32_t off = a.tap_off[tap];
-          for (int kc = 0; kc < a.kchunks; ++kc, ++it) {
-            const int s = it % S;
-            if (it >= S) ok = mbar_wait(&empty_bar[s], (uint32_t)(((it / S) - 1) & 1), abort_flag);
+          for (int kc = 0; kc < a.kchunks; ++kc) {
+            const uint32_t sa = stage_begin();
             if (!ok) break;
-            const uint32_t sa = smem_base + (uint32_t)s * C::STAGE_BYTES;
-            mbar_expect_tx(&full_bar[s], (uint32_t)C::STAGE_BYTES);
             tma_load_im2col_4d(sa, &a.map_a, &full_bar[s], kc * KC, w0, h0, b, (uint16_t)(off & 0xffffu),
                                (uint16_t)(off >> 16));
-            tma_load_2d(sa + A_STAGE_BYTES, &a.map_b, &full_bar[s], tap * a.Cin + kc * KC, nt * BN);
+            if (!bres) tma_load_2d(sa + A_STAGE_BYTES, &a.map_b, &full_bar[s], tap * a.Cin + kc * KC, nt * BN);
+            stage_end();
           }
         }
         // second input: one (0,0) tap over the output grid, weight columns after the ntaps*Cin of the main input
-        for (int kc = 0; kc < a.kchunks2 && ok; ++kc, ++it) {
-          const int s = it % S;
-          if (it >= S) ok = mbar_wait(&empty_bar[s], (uint32_t)(((it / S) - 1) & 1), abort_flag);
+        for (int kc = 0; kc < a.kchunks2 && ok; ++kc) {
+          const uint32_t sa = stage_begin();
           if (!ok) break;
-          const uint32_t sa = smem_base + (uint32_t)s * C::STAGE_BYTES;
-          mbar_expect_tx(&full_bar[s], (uint32_t)C::STAGE_BYTES);
           tma_load_im2col_4d(sa, &a.map_a2, &full_bar[s], kc * KC, ox, oy, b, (uint16_t)0, (uint16_t)0);
-          tma_load_2d(sa + A_STAGE_BYTES, &a.map_b, &full_bar[s], a.ntaps * a.Cin + kc * KC, nt * BN);
+          if (!bres) tma_load_2d(sa + A_STAGE_BYTES, &a.map_b, &full_bar[s], a.ntaps * a.Cin + kc * KC, nt * BN);
+          stage_end();
         }
-        if (!ok) break;
       }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    int it = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+    int s = 0, round = 0, tcount = 0;
+    bool ok = true;
+    if (bres) ok = mbar_wait(bres_bar, 0u, abort_flag);
+    for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x, ++tcount) {
       const int acc = tcount & 1;
-      bool ok = true;
       if (tcount >= 2) ok = mbar_wait(&tempty_bar[acc], (uint32_t)(((tcount >> 1) - 1) & 1), abort_flag);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C::ACC_STRIDE);
-      for (int kb = 0; kb < nkb && ok; ++kb, ++it) {
-        const int s = it % S;
-        ok = mbar_wait(&full_bar[s], (uint32_t)((it / S) & 1), abort_flag);
+      for (int kb = 0; kb < nkb && ok; ++kb) {
+        ok = mbar_wait(&full_bar[s], (uint32_t)(round & 1), abort_flag);
         tc_fence_after();
         if (lane == 0 && ok) {
-          const uint32_t a_addr = smem_base + (uint32_t)s * C::STAGE_BYTES;
+          const uint32_t a_addr = ring_base + (uint32_t)s * stage_bytes;
           const uint64_t adesc = make_desc_kmajor<RB>(a_addr);
-          const uint64_t bdesc = make_desc_kmajor<RB>(a_addr + A_STAGE_BYTES);
+          const uint64_t bdesc = make_desc_kmajor<RB>(bres ? smem_base + (uint32_t)(kb * C::B_STAGE_BYTES)
+                                                           : a_addr + A_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < RB / 32; ++k)
             umma<HALF>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (kb | k) ? 1u : 0u);
@@ -240,8 +265,8 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
           if (kb == nkb - 1) umma_commit(&tfull_bar[acc]);
         }
         __syncwarp();
+        if (++s == s_run) { s = 0; ++round; }
       }
-      if (!ok) break;
     }
     tc_fence_before();
   } else {
@@ -252,7 +277,7 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
     const int ew = warp - 2;
     const int q = warp & 3;
     const int par = ew >> 2;
-    float* slab = reinterpret_cast<float*>(smem + C::EPI_OFFSET) + (size_t)ew * 32 * SSTR;
+    float* slab = reinterpret_cast<float*>(smem + a.epi_off) + (size_t)ew * 32 * SSTR;
     constexpr int NSLAB = BN / SLAB;
     constexpr int LPR = SLAB / 4;                             // lanes per row in the coalesced pass
     constexpr int RPI = 32 / LPR;                             // rows per iteration
@@ -387,18 +412,51 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
   }
 }
 
+// Resident weights pay off when a CTA runs several tiles against the same [nkb][BN x RB] weight block and that block
+// leaves room for a >= 4-deep A ring: L2 -> smem traffic per tile drops from A + B to A.
+inline int g_bres_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CNB_CONV_BRES");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
 template <int BN, bool HALF, int EPI, int RB>
-static int launch_epi(const TmaArgs& a, int num_sms, cudaStream_t st) {
+static int launch_epi(const TmaArgs& a_in, int num_sms, cudaStream_t st) {
   using C = Cfg<BN, RB>;
   static bool attr_set = false;
   if (!attr_set) {
     CNB_CUDA(cudaFuncSetAttribute(conv_tma_kernel<BN, HALF, EPI, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  C::TOTAL));
+                                  SMEM_BUDGET));
     attr_set = true;
   }
+  TmaArgs a = a_in;
   const int ntiles = a.tiles_m * a.tiles_n;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  conv_tma_kernel<BN, HALF, EPI, RB><<<grid, NUM_THREADS, C::TOTAL, st>>>(a);
+  const int nkb = a.ntaps * a.kchunks + a.kchunks2;
+  const int b_res_bytes = nkb * C::B_STAGE_BYTES;
+  const int room = SMEM_BUDGET - 1024 - C::EPI_BYTES - C::BAR_BYTES - b_res_bytes;
+  int s_res = room > 0 ? room / C::A_STAGE_BYTES : 0;
+  if (s_res > C::S) s_res = C::S;
+  size_t smem_bytes;
+  if (g_bres_enabled() && a.tiles_n == 1 && ntiles >= 3 * grid && s_res >= 4 && b_res_bytes % 1024 == 0) {
+    a.bres = 1;
+    a.s_run = s_res;
+    a.ring_off = b_res_bytes;
+    a.stage_bytes = C::A_STAGE_BYTES;
+    a.epi_off = a.ring_off + s_res * C::A_STAGE_BYTES;
+  } else {
+    a.bres = 0;
+    a.s_run = C::S;
+    a.ring_off = 0;
+    a.stage_bytes = C::STAGE_BYTES;
+    a.epi_off = C::EPI_OFFSET;
+  }
+  a.bar_off = a.epi_off + C::EPI_BYTES;
+  smem_bytes = (size_t)a.bar_off + C::BAR_BYTES + 1024;
+  conv_tma_kernel<BN, HALF, EPI, RB><<<grid, NUM_THREADS, smem_bytes, st>>>(a);
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }

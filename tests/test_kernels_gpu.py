@@ -52,6 +52,8 @@ CONV_CASES = [
     # direct small-channel kernels: conv_in / hint conv0 / conv_out shapes of the three configs
     ("3x3", 3, 4, 256, 8, 8), ("3x3", 2, 128, 4, 8, 8), ("3x3", 2, 16, 3, 9, 11), ("1x1", 2, 4, 4, 5, 5),
     ("3x3", 2, 3, 16, 12, 12), ("4x4s2", 2, 3, 32, 8, 8),
+    # >= 3 tiles per CTA on 148 SMs: the resident-weights variant of the TMA kernel
+    ("3x3", 80, 64, 64, 28, 28), ("1x1", 75, 64, 192, 28, 28), ("3x3", 77, 16, 16, 28, 28), ("3x3", 300, 128, 32, 14, 14),
 ]
 
 
@@ -178,7 +180,7 @@ def test_attention_f16(pk, B, L, E, heads):
 
 
 @pytest.mark.parametrize("B,C,Cx,Cout,H,W", [(3, 64, 64, 64, 14, 14), (2, 64, 32, 64, 28, 28), (5, 128, 256, 128, 7, 7),
-                                             (2, 16, 64, 16, 9, 11), (33, 32, 32, 32, 14, 14)])
+                                             (2, 16, 64, 16, 9, 11), (33, 32, 32, 32, 14, 14), (76, 64, 32, 64, 28, 28)])
 def test_conv_k_concat_second_input(pk, B, C, Cx, Cout, H, W):
     """3x3 conv over h plus a 1x1 conv over a second input x folded in as extra K (resnet residual_input_conv)."""
     ops, rt = pk
