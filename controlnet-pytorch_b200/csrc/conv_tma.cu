@@ -127,8 +127,65 @@ int conv2d_tma(const cnb_conv_params* p, cudaStream_t st) {
   const int lower[2] = {dxmin, dymin};
   const int upper[2] = {dxmin + (p->OW - 1) * p->stride + 1 - p->W, dymin + (p->OH - 1) * p->stride + 1 - p->H};
 
-  // ---- activations: [B, H, W, ldi] viewed as (C, W, H, N), im2col box = 128 pixels x kc channels
+  // ---- halo mode: 3x3 / stride 1 / pad 1 with resident weights; the input tile is loaded once per channel chunk
+  const int bn_h = pick_bn(p->Cout);
+  bool halo = false;
+  int Wp = p->W + 2, R = 0, halo_stage = 0;
   {
+    static int halo_on = -1;
+    if (halo_on < 0) {
+      const char* e = getenv("CNB_CONV_HALO");
+      halo_on = e ? atoi(e) : 1;
+    }
+    bool std3 = p->ntaps == 9 && p->stride == 1 && p->OH == p->H && p->OW == p->W && p->oy_mul == 1 && p->ox_mul == 1 &&
+                p->oy_add == 0 && p->ox_add == 0 && p->OHf == p->OH && p->OWf == p->OW && p->Cout == bn_h;
+    for (int t = 0; t < 9 && std3; ++t) std3 = p->dy[t] == t / 3 - 1 && p->dx[t] == t % 3 - 1;
+    if (halo_on && std3 && Wp <= 64 && p->W >= 12) {
+      R = BM / Wp;
+      const int tiles_y = ceil_div(p->H, R);
+      const double useful = (double)p->H * p->W / ((double)tiles_y * BM);
+      const int nkb_all = 9 * (p->Cin / kc) + (p->in2 ? ceil_div(p->Cin2, kc) : 0);
+      const int b_res = (nkb_all * bn_h * rb + 1023) / 1024 * 1024;
+      halo_stage = ((BM + 2 * Wp + 2) * rb + 1023) / 1024 * 1024;
+      const int room = SMEM_BUDGET - 1024 - 36864 - 256 - b_res;
+      halo = useful >= 0.7 && room >= 3 * halo_stage && (long long)p->B * tiles_y >= 2 * g_num_sms;
+    }
+  }
+  if (halo) {
+    const cuuint64_t dims[4] = {(cuuint64_t)p->Cin, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->B};
+    const cuuint64_t strides[3] = {(cuuint64_t)p->ldi * elt, (cuuint64_t)p->W * p->ldi * elt,
+                                   (cuuint64_t)p->H * p->W * p->ldi * elt};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)Wp, (cuuint32_t)(R + 2), 1};
+    void* base = const_cast<char*>(reinterpret_cast<const char*>(p->in) + (size_t)p->in_coff * elt);
+    CUresult r = g_encode_tiled(&a.map_a, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base,
+                                dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(halo input) failed (%d): Cin=%d W=%d H=%d B=%d box=(%d,%d,%d)", (int)r, p->Cin,
+                p->W, p->H, p->B, kc, Wp, R + 2);
+      return CNB_ERR_CUDA;
+    }
+    if (p->in2) {
+      const cuuint64_t dims2[4] = {(cuuint64_t)p->Cin2, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->B};
+      const cuuint64_t strides2[3] = {(cuuint64_t)p->ldi2 * elt, (cuuint64_t)p->W * p->ldi2 * elt,
+                                      (cuuint64_t)p->H * p->W * p->ldi2 * elt};
+      const cuuint32_t box2[4] = {(cuuint32_t)kc, (cuuint32_t)Wp, (cuuint32_t)R, 1};
+      void* base2 = const_cast<char*>(reinterpret_cast<const char*>(p->in2) + (size_t)p->in2_coff * elt);
+      r = g_encode_tiled(&a.map_a2, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base2,
+                         dims2, strides2, box2, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(halo second input) failed (%d)", (int)r);
+        return CNB_ERR_CUDA;
+      }
+      a.kchunks2 = ceil_div(p->Cin2, kc);
+    }
+    a.halo = 1; a.Wp = Wp; a.R = R; a.tiles_y = ceil_div(p->H, R); a.H = p->H; a.W = p->W;
+    a.halo_stage_bytes = halo_stage;
+  }
+  // ---- activations: [B, H, W, ldi] viewed as (C, W, H, N), im2col box = 128 pixels x kc channels
+  if (!halo) {
     const cuuint64_t dims[4] = {(cuuint64_t)p->Cin, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->B};
     const cuuint64_t strides[3] = {(cuuint64_t)p->ldi * elt, (cuuint64_t)p->W * p->ldi * elt,
                                    (cuuint64_t)p->H * p->W * p->ldi * elt};
@@ -148,7 +205,7 @@ int conv2d_tma(const cnb_conv_params* p, cudaStream_t st) {
     if (g_driver_version <= 13010 && bytes < 131072) reinterpret_cast<uint64_t*>(&a.map_a)[1] &= ~(1llu << 21);
   }
   // ---- optional second input: [B, OH, OW, ldi2], a single (0,0) tap on the output grid
-  if (p->in2) {
+  if (p->in2 && !halo) {
     const int zero2[2] = {0, 0};
     const cuuint64_t dims[4] = {(cuuint64_t)p->Cin2, (cuuint64_t)p->OW, (cuuint64_t)p->OH, (cuuint64_t)p->B};
     const cuuint64_t strides[3] = {(cuuint64_t)p->ldi2 * elt, (cuuint64_t)p->OW * p->ldi2 * elt,
@@ -194,7 +251,7 @@ int conv2d_tma(const cnb_conv_params* p, cudaStream_t st) {
   a.temb_ld = p->temb_ld; a.temb_per_sample = p->temb_per_sample; a.act = p->act; a.out_f16 = p->out_dtype == 1; a.res_f16 = p->res_dtype == 1;
   a.Cin = p->Cin; a.ntaps = p->ntaps; a.kchunks = p->Cin / kc;
   a.stride = p->stride; a.lower_w = dxmin; a.lower_h = dymin;
-  a.tiles_m = ceil_div(a.M, BM); a.tiles_n = p->Cout / bn;
+  a.tiles_m = halo ? p->B * a.tiles_y : ceil_div(a.M, BM); a.tiles_n = p->Cout / bn;
   return half ? conv_tma_launch_f16(rb, bn, a, g_num_sms, st) : conv_tma_launch_tf32(rb, bn, a, g_num_sms, st);
 }
 

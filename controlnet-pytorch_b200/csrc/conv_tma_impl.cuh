@@ -50,6 +50,10 @@ struct alignas(64) TmaArgs {
   int stride, lower_w, lower_h;
   int tiles_m, tiles_n;
   // shared-memory plan (runtime: the resident-weights variant trades ring depth for a [nkb][BN x RB] weight area)
+  // halo mode (3x3, stride 1, pad 1): a stage holds (R+2) x (W+2) input pixels of one channel chunk, loaded ONCE by a
+  // tiled TMA (zero fill outside the image), and the 9 taps are 9 MMAs whose A descriptors start dy*(W+2)+dx rows
+  // further into the same tile.  GEMM rows are padded-flat positions y*(W+2)+x of R image rows; x >= W is discarded.
+  int halo, Wp, R, tiles_y, H, W, halo_stage_bytes;
   int bres;         // 1 = the whole packed weight tile stays resident in smem, the ring carries A stages only
   int s_run;        // ring depth actually used (<= Cfg::S)
   int ring_off, stage_bytes, epi_off, bar_off;
@@ -66,6 +70,13 @@ __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const void* map
       " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n),
         "h"(off_w), "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_tiled_4d(uint32_t dst, const void* map, uint64_t* bar, int c, int w, int h,
+                                                  int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* map, uint64_t* bar, int x, int y) {
@@ -132,7 +143,8 @@ struct Cfg {
 };
 
 // EPI selects the epilogue: 0 = dense fp32 out, 1 = dense fp32 out + fp32 residual, 2 = dense fp16 out,
-// 4 = dense fp16 out + fp16 residual (the fp16 activation stream), 3 = generic.
+// 4 = dense fp16 out + fp16 residual (the fp16 activation stream), 5 = halo tiles with fp16 out (+ fp16 residual),
+// 3 = generic.
 template <int BN, bool HALF, int EPI, int RB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tma_kernel(const __grid_constant__ TmaArgs a) {
@@ -200,7 +212,7 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
         for (int kc = 0; kc < a.kchunks2; ++kc, ++kb)
           tma_load_2d(smem_base + (uint32_t)(kb * C::B_STAGE_BYTES), &a.map_b, bres_bar, a.ntaps * a.Cin + kc * KC, 0);
       }
-      const uint32_t tx = bres ? (uint32_t)A_STAGE_BYTES : (uint32_t)C::STAGE_BYTES;
+      uint32_t tx = bres ? (uint32_t)A_STAGE_BYTES : (uint32_t)C::STAGE_BYTES;
       int s = 0, round = 0;
       bool ok = true;
       auto stage_begin = [&]() -> uint32_t {      // waits for the slot, arms its barrier, returns its smem address
@@ -211,6 +223,26 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
       auto stage_end = [&]() {
         if (++s == s_run) { s = 0; ++round; }
       };
+      if (a.halo) {
+        for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
+          const int b = tile / a.tiles_y;
+          const int y0 = (tile - b * a.tiles_y) * a.R;
+          tx = (uint32_t)((a.R + 2) * a.Wp * RB);
+          for (int kc = 0; kc < a.kchunks && ok; ++kc) {
+            const uint32_t sa = stage_begin();
+            if (!ok) break;
+            tma_load_tiled_4d(sa, &a.map_a, &full_bar[s], kc * KC, -1, y0 - 1, b);
+            stage_end();
+          }
+          tx = (uint32_t)(a.R * a.Wp * RB);
+          for (int kc = 0; kc < a.kchunks2 && ok; ++kc) {
+            const uint32_t sa = stage_begin();
+            if (!ok) break;
+            tma_load_tiled_4d(sa, &a.map_a2, &full_bar[s], kc * KC, 0, y0, b);
+            stage_end();
+          }
+        }
+      } else
       for (int tile = blockIdx.x; tile < ntiles && ok; tile += gridDim.x) {
         const int mt = tile / a.tiles_n, nt = tile - mt * a.tiles_n;
         const int m0 = mt * BM;
@@ -250,6 +282,42 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
       if (tcount >= 2) ok = mbar_wait(&tempty_bar[acc], (uint32_t)(((tcount >> 1) - 1) & 1), abort_flag);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * C::ACC_STRIDE);
+      if (a.halo) {
+        // One thread issues 9 taps x RB/32 MMAs per stage, so the descriptor arithmetic is kept to 64-bit adds: the
+        // tap's row shift and the weight block's offset are both expressed in the descriptor's 16-byte address units.
+        const int nstage = a.kchunks + a.kchunks2;
+        const uint64_t b_first = make_desc_kmajor<RB>(smem_base);
+        const uint64_t b_blk = (uint64_t)(C::B_STAGE_BYTES >> 4);
+        const uint64_t b_tap = b_blk * (uint64_t)a.kchunks;          // consecutive taps of one channel chunk
+        const uint64_t a_row = (uint64_t)(a.Wp * RB) >> 4;           // one padded image row
+        for (int st = 0; st < nstage && ok; ++st) {
+          ok = mbar_wait(&full_bar[s], (uint32_t)(round & 1), abort_flag);
+          tc_fence_after();
+          if (lane == 0 && ok) {
+            const uint64_t abase = make_desc_kmajor<RB>(ring_base + (uint32_t)s * stage_bytes);
+            if (st < a.kchunks) {
+              const uint64_t bbase = b_first + b_blk * (uint64_t)st;
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint64_t adesc = abase + a_row * (uint64_t)(tap / 3) + (uint64_t)((tap % 3) * (RB >> 4));
+                const uint64_t bdesc = bbase + b_tap * (uint64_t)tap;
+#pragma unroll
+                for (int k = 0; k < RB / 32; ++k)
+                  umma<HALF>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, (st | tap | k) ? 1u : 0u);
+              }
+            } else {
+              const uint64_t bdesc = b_first + b_tap * 9ull + b_blk * (uint64_t)(st - a.kchunks);
+#pragma unroll
+              for (int k = 0; k < RB / 32; ++k)
+                umma<HALF>(d_tmem, abase + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), IDESC, 1u);
+            }
+            umma_commit(&empty_bar[s]);
+            if (st == nstage - 1) umma_commit(&tfull_bar[acc]);
+          }
+          __syncwarp();
+          if (++s == s_run) { s = 0; ++round; }
+        }
+      } else
       for (int kb = 0; kb < nkb && ok; ++kb) {
         ok = mbar_wait(&full_bar[s], (uint32_t)(round & 1), abort_flag);
         tc_fence_after();
@@ -292,7 +360,21 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
       const int n0 = nt * BN;
       long long pix = -1;
       int b = 0;
-      if (EPI == 3) {
+      int pixi = -1;                                          // EPI 5: 32-bit output pixel index of this lane's row
+      if (EPI == 5) {
+        const int r = q * 32 + lane;
+        const int bb = tile / a.tiles_y;
+        const int yy = r / a.Wp, xx = r - yy * a.Wp;
+        const int y = (tile - bb * a.tiles_y) * a.R + yy;
+        if (yy < a.R && xx < a.W && y < a.H) pixi = (bb * a.H + y) * a.W + xx;
+      }
+      if (EPI == 3 && a.halo) {
+        const int r = q * 32 + lane;                          // padded-flat position inside the tile
+        b = tile / a.tiles_y;
+        const int yy = r / a.Wp, xx = r - yy * a.Wp;
+        const int y = (tile - b * a.tiles_y) * a.R + yy;
+        if (yy < a.R && xx < a.W && y < a.H) pix = ((long long)b * a.H + y) * a.W + xx;
+      } else if (EPI == 3) {
         const int m = m_w + lane;
         if (m < M) {
           b = m / a.OHW;
@@ -335,7 +417,26 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
           const float4 t = __ldg(reinterpret_cast<const float4*>(temb_row + n));
           bv.x += t.x; bv.y += t.y; bv.z += t.z; bv.w += t.w;
         }
-        if (EPI != 3) {
+        if (EPI == 5) {
+          // ---- halo tiles, fp16 activation stream: row -> pixel through one shuffle, fp16 out (+ fp16 residual)
+          const __half* resh = reinterpret_cast<const __half*>(a.residual);
+          __half* outh = reinterpret_cast<__half*>(a.out);
+#pragma unroll
+          for (int i = 0; i < 32 / RPI; ++i) {
+            const int rp = __shfl_sync(0xffffffffu, pixi, i * RPI + sub_r);
+            if (rp >= 0) {
+              float4 o = *reinterpret_cast<const float4*>(slab + (size_t)(i * RPI + sub_r) * SSTR + sub_c);
+              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+              if (resh) {
+                const float4 t = ld_half4(resh + (size_t)rp * ldr + a.res_coff + n);
+                o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+              }
+              const __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
+              *reinterpret_cast<uint2*>(outh + (size_t)rp * ldo + a.out_coff + n) =
+                  make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+            }
+          }
+        } else if (EPI != 3) {
           // ---- dense output: GEMM row m is output pixel m
           const int rows_left = M - m_w - sub_r;              // row rr + sub_r is valid iff rr < rows_left
           const float* sp = slab + (size_t)sub_r * SSTR + sub_c;
@@ -436,12 +537,24 @@ static int launch_epi(const TmaArgs& a_in, int num_sms, cudaStream_t st) {
   const int ntiles = a.tiles_m * a.tiles_n;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
   const int nkb = a.ntaps * a.kchunks + a.kchunks2;
-  const int b_res_bytes = nkb * C::B_STAGE_BYTES;
+  const int b_res_bytes = (nkb * C::B_STAGE_BYTES + 1023) / 1024 * 1024;   // ring starts on a 1 KB boundary
   const int room = SMEM_BUDGET - 1024 - C::EPI_BYTES - C::BAR_BYTES - b_res_bytes;
   int s_res = room > 0 ? room / C::A_STAGE_BYTES : 0;
   if (s_res > C::S) s_res = C::S;
   size_t smem_bytes;
-  if (g_bres_enabled() && a.tiles_n == 1 && ntiles >= 3 * grid && s_res >= 4 && b_res_bytes % 1024 == 0) {
+  if (a.halo) {
+    int s_h = room > 0 ? room / a.halo_stage_bytes : 0;
+    if (s_h > C::S) s_h = C::S;
+    if (s_h < 2) {
+      set_error("conv_tma: halo plan does not fit shared memory (host-side check out of sync)");
+      return CNB_ERR_UNSUPPORTED;
+    }
+    a.bres = 1;
+    a.s_run = s_h;
+    a.ring_off = b_res_bytes;
+    a.stage_bytes = a.halo_stage_bytes;
+    a.epi_off = a.ring_off + s_h * a.halo_stage_bytes;
+  } else if (g_bres_enabled() && a.tiles_n == 1 && ntiles >= 3 * grid && s_res >= 4) {
     a.bres = 1;
     a.s_run = s_res;
     a.ring_off = b_res_bytes;
@@ -463,8 +576,11 @@ static int launch_epi(const TmaArgs& a_in, int num_sms, cudaStream_t st) {
 
 template <int BN, bool HALF, int RB>
 static int launch(const TmaArgs& a, int num_sms, cudaStream_t st) {
-  const bool dense = a.oy_mul == 1 && a.ox_mul == 1 && a.oy_add == 0 && a.ox_add == 0 && a.OHf * a.OWf == a.OHW;
+  const bool dense = !a.halo && a.oy_mul == 1 && a.ox_mul == 1 && a.oy_add == 0 && a.ox_add == 0 &&
+                     a.OHf * a.OWf == a.OHW;
   const bool simple = dense && a.act == 0 && !(a.temb && a.temb_per_sample);
+  if (a.halo && a.act == 0 && !(a.temb && a.temb_per_sample) && a.out_f16 && (!a.residual || a.res_f16))
+    return launch_epi<BN, HALF, 5, RB>(a, num_sms, st);
   if (simple && !a.out_f16 && !a.residual) return launch_epi<BN, HALF, 0, RB>(a, num_sms, st);
   if (simple && !a.out_f16 && a.residual && !a.res_f16) return launch_epi<BN, HALF, 1, RB>(a, num_sms, st);
   if (simple && a.out_f16 && !a.residual) return launch_epi<BN, HALF, 2, RB>(a, num_sms, st);

@@ -60,11 +60,11 @@ if what in ("conv", "all"):
                 x = x.half()
             bias = torch.randn(cout, device="cuda")
             oh = ops.out_size(kind, hw)
-            out = torch.empty(B, oh, oh, cout, device="cuda")
+            out = torch.empty(B, oh, oh, cout, device="cuda", dtype=torch.float16 if (half and os.environ.get("CB_OUT16", "1") == "1") else torch.float32)
             ms = timeit(lambda: ops.conv(x, w, kind, cout, bias=bias, out=out, mode=mode, weight_lp=wl,
                                       act=int(os.environ.get('CB_ACT', '0'))))
             fl = 2.0 * B * oh * oh * k * cin * cout
-            by = x.numel() * x.element_size() + 4.0 * out.numel() + w.numel() * (2 if half else 4)
+            by = x.numel() * x.element_size() + out.numel() * out.element_size() + w.numel() * (2 if half else 4)
             print(f"conv[{name}] {kind} {cin}->{cout} @{hw}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:8.1f} TFLOP/s  "
                   f"{by / ms / 1e6:8.1f} GB/s(min-traffic)", flush=True)
 
