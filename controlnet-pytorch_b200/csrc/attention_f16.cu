@@ -156,19 +156,22 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
   const uint32_t v_lane_off = (uint32_t)(((lm & 1) * 8 + lr) * STRIDE + (lm >> 1) * 8) * 2u;
   constexpr uint32_t ONES = 0x3C003C00u;         // half2(1, 1)
 
-  // one key tile; MASK = the (only) tile that may contain keys >= L
-  auto tile_body = [&](int t, auto mask_tag) {
+  // one key tile; MASK = the (only) tile that may contain keys >= L; NG = 16-key groups of the tile that hold any
+  // valid key (the ragged last tile skips its fully padded groups: 784 = 12 x 64 + 16 keys costs 12.25 tiles, not 13)
+  auto tile_body = [&](int t, auto mask_tag, auto ng_tag) {
     constexpr bool MASK = decltype(mask_tag)::value;
+    constexpr int NG = decltype(ng_tag)::value;
+    constexpr int NTA = NG * 2;                    // active S column tiles
     const int stage = t % 3;
     const uint32_t sK = smem_u + (uint32_t)(stage * 2 * TILE) * 2u;
     const uint32_t sV = sK + (uint32_t)TILE * 2u;
 
     // ---- S = Q K^T  (16 x BK per warp)
-    float s[NT][4];
+    float s[NTA][4];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    for (int nt = 0; nt < NTA; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
 #pragma unroll
-    for (int np = 0; np < NT / 2; ++np) {
+    for (int np = 0; np < NG; ++np) {
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         uint32_t r0, r1, r2, r3;
@@ -180,7 +183,7 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
     if (MASK) {
       const int kbase = t * BK;
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
+      for (int nt = 0; nt < NTA; ++nt) {
         const int key = kbase + nt * 8 + 2 * q4;
         if (key >= L) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
         if (key + 1 >= L) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
@@ -189,7 +192,7 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
     // ---- online softmax (rows g and g + 8)
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
+    for (int nt = 0; nt < NTA; ++nt) {
       mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
       mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
@@ -206,7 +209,7 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
     for (int i = 0; i < NV; ++i) { o[i][0] *= cr0; o[i][1] *= cr0; o[i][2] *= cr1; o[i][3] *= cr1; }
     // ---- P = exp2(.) packed to fp16 = A fragments of the second MMA;  O += P V,  l += P 1
 #pragma unroll
-    for (int kk = 0; kk < BK / 16; ++kk) {
+    for (int kk = 0; kk < NG; ++kk) {
       uint32_t pa[4];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -241,6 +244,7 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
 
   // 3-stage ring, ONE block barrier per tile: the barrier that publishes tile t also proves every warp has finished
   // tile t-1, whose stage is exactly the one tile t+2 is loaded into right after it.
+  const bool active = q0 < L;
   load_tile(0, 0);
   if (ntiles > 1) load_tile(1, 1);
   const bool ragged = (L % BK) != 0;
@@ -249,8 +253,17 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
     else asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (t + 2 < ntiles) load_tile(t + 2, (t + 2) % 3);
-    if (ragged && t == ntiles - 1) tile_body(t, std::true_type{});
-    else tile_body(t, std::false_type{});
+    if (active) {                                  // warps whose 16 query rows are all padding only help with the loads
+      if (ragged && t == ntiles - 1) {
+        const int groups = (L - t * BK + 15) / 16;
+        if (groups == 1) tile_body(t, std::true_type{}, std::integral_constant<int, 1>{});
+        if constexpr (BK >= 32) { if (groups == 2) tile_body(t, std::true_type{}, std::integral_constant<int, 2>{}); }
+        if constexpr (BK >= 48) { if (groups == 3) tile_body(t, std::true_type{}, std::integral_constant<int, 3>{}); }
+        if constexpr (BK >= 64) { if (groups == 4) tile_body(t, std::true_type{}, std::integral_constant<int, 4>{}); }
+      } else {
+        tile_body(t, std::false_type{}, std::integral_constant<int, BK / 16>{});
+      }
+    }
   }
 
   // ---- normalise and store
