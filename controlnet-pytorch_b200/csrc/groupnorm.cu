@@ -12,6 +12,18 @@
 
 namespace cnb {
 
+// SiLU for fp16 outputs: x * sigmoid(x) = h + h * tanh(h) with h = x / 2 -- ONE MUFU op (tanh.approx, ~2^-11 relative,
+// the rounding of the fp16 result) instead of ex2 + rcp.  At B = 1024 the 64-channel 28x28 tensor alone carries 51 M
+// activations: two MUFU ops each would cost 23 us of XU time, as much as the kernel's DRAM time.
+__device__ __forceinline__ float silu_tanh(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+template <bool HALF>
+__device__ __forceinline__ float silu_out(float x) { return HALF ? silu_tanh(x) : silu_f(x); }
+
 template <bool HALF> struct OutVec;
 template <> struct OutVec<false> {
   using type = float4;
@@ -43,7 +55,11 @@ template <> struct InVec<true> {
   static __device__ __forceinline__ float4 load_cs(const uint2* p) { return widen(__ldcs(p)); }
 };
 
-template <bool SILU, bool HALF, bool HIN>
+// STAGE: the fp16 slab of the sample is first brought into shared memory by ONE bulk copy (cp.async.bulk + mbarrier, no
+// per-thread load instructions, the whole slab in flight at once) and the three sweeps read smem; with two CTAs per SM
+// the copy of one sample overlaps the arithmetic of the other, so the kernel runs at DRAM speed instead of at the
+// latency of three dependent sweeps.
+template <bool SILU, bool HALF, bool HIN, bool STAGE>
 __global__ void __launch_bounds__(1024)
 groupnorm_nhwc_kernel(const void* __restrict__ x, void* __restrict__ y, const float* __restrict__ gamma,
                       const float* __restrict__ beta, int HW, int C, int G, float eps) {
@@ -65,7 +81,31 @@ groupnorm_nhwc_kernel(const void* __restrict__ x, void* __restrict__ y, const fl
     const typename IV::type* p;
     __device__ __forceinline__ float4 operator[](size_t i) const { return IV::load(p + i); }
   };
-  const XS xs{reinterpret_cast<const typename IV::type*>(x) + (size_t)blockIdx.x * HW * C4};
+  const typename IV::type* src = reinterpret_cast<const typename IV::type*>(x) + (size_t)blockIdx.x * HW * C4;
+  if (STAGE) {
+    __shared__ __align__(8) uint64_t bar;
+    typename IV::type* slab = reinterpret_cast<typename IV::type*>(
+        reinterpret_cast<char*>(sm) + (((size_t)(R * C + C + 2 * G) * sizeof(float) + 127) / 128) * 128);
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+    const uint32_t bytes = (uint32_t)((size_t)HW * C4 * sizeof(typename IV::type));
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((uint32_t)__cvta_generic_to_shared(slab)), "l"(src), "r"(bytes), "r"(bar_a)
+                   : "memory");
+    }
+    __syncthreads();                                       // barrier object initialised before anyone polls it
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(bar_a) : "memory");
+    }
+    src = slab;
+  }
+  const XS xs{src};
   using OV = OutVec<HALF>;
   typename OV::type* ys = reinterpret_cast<typename OV::type*>(y) + (size_t)blockIdx.x * HW * C4;
   const float inv_n = 1.0f / (float)(cg * HW);
@@ -155,7 +195,7 @@ groupnorm_nhwc_kernel(const void* __restrict__ x, void* __restrict__ y, const fl
   auto apply = [&](float4 v) {
     float4 o;
     o.x = fmaf(v.x, a0, b0); o.y = fmaf(v.y, a1, b1); o.z = fmaf(v.z, a2, b2); o.w = fmaf(v.w, a3, b3);
-    if (SILU) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+    if (SILU) { o.x = silu_out<HALF>(o.x); o.y = silu_out<HALF>(o.y); o.z = silu_out<HALF>(o.z); o.w = silu_out<HALF>(o.w); }
     return o;
   };
   pidx = r0;
@@ -302,7 +342,7 @@ groupnorm_reg_kernel(const void* __restrict__ x, void* __restrict__ y, const flo
     if (row < nrows) {
       float4 o;
       o.x = fmaf(v[k].x, a0, b0); o.y = fmaf(v[k].y, a1, b1); o.z = fmaf(v[k].z, a2, b2); o.w = fmaf(v[k].w, a3, b3);
-      if (SILU) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+      if (SILU) { o.x = silu_out<HALF>(o.x); o.y = silu_out<HALF>(o.y); o.z = silu_out<HALF>(o.z); o.w = silu_out<HALF>(o.w); }
       ys[(size_t)row * C4 + col] = OV::pack(o);
     }
   }
@@ -356,12 +396,116 @@ static int launch_reg(const void* x, void* y, const float* gamma, const float* b
   return CNB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Warp-per-group variant for small groups (<= 32 lanes x 13 vectors, >= 16 channels per group): one warp owns one
+// (sample, group), keeps it in registers, reduces with shuffles only -- no shared memory, no block barrier, so the
+// 7x7 / 14x14 levels (45 of the 87 GroupNorms of an MNIST step) stop being bound by barrier latency.
+// ---------------------------------------------------------------------------------------------------------
+template <int KMAX, bool SILU, bool HALF, bool HIN>
+__global__ void __launch_bounds__(256)
+groupnorm_warp_kernel(const void* __restrict__ x, void* __restrict__ y, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, int BG, int HW, int C, int G, float eps) {
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= BG) return;
+  const int lane = threadIdx.x & 31;
+  const int b = wid / G, g = wid - b * G;
+  const int C4 = C >> 2;
+  const int LPP = (C / G) >> 2;          // lanes per pixel (4-channel vectors per group)
+  const int PPI = 32 / LPP;              // pixels per iteration
+  const int lc = lane % LPP, lp = lane / LPP;
+  using IV = InVec<HIN>;
+  using OV = OutVec<HALF>;
+  const size_t base = (size_t)b * HW * C4 + (size_t)g * LPP + lc;
+  const typename IV::type* xs = reinterpret_cast<const typename IV::type*>(x) + base;
+  typename OV::type* ys = reinterpret_cast<typename OV::type*>(y) + base;
+
+  float4 v[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int p = lp + k * PPI;
+    v[k] = p < HW ? IV::load_cs(xs + (size_t)p * C4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  const float inv_n = 1.0f / (float)((C / G) * HW);
+  const float mean = warp_sum(s) * inv_n;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    if (lp + k * PPI < HW) {
+      float d;
+      d = v[k].x - mean; q = fmaf(d, d, q);
+      d = v[k].y - mean; q = fmaf(d, d, q);
+      d = v[k].z - mean; q = fmaf(d, d, q);
+      d = v[k].w - mean; q = fmaf(d, d, q);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) * inv_n + eps);
+  const float4 ga = reinterpret_cast<const float4*>(gamma)[g * LPP + lc];
+  const float4 be = reinterpret_cast<const float4*>(beta)[g * LPP + lc];
+  const float a0 = rstd * ga.x, a1 = rstd * ga.y, a2 = rstd * ga.z, a3 = rstd * ga.w;
+  const float b0 = be.x - mean * a0, b1 = be.y - mean * a1, b2 = be.z - mean * a2, b3 = be.w - mean * a3;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    const int p = lp + k * PPI;
+    if (p < HW) {
+      float4 o;
+      o.x = fmaf(v[k].x, a0, b0); o.y = fmaf(v[k].y, a1, b1); o.z = fmaf(v[k].z, a2, b2); o.w = fmaf(v[k].w, a3, b3);
+      if (SILU) { o.x = silu_out<HALF>(o.x); o.y = silu_out<HALF>(o.y); o.z = silu_out<HALF>(o.z); o.w = silu_out<HALF>(o.w); }
+      ys[(size_t)p * C4] = OV::pack(o);
+    }
+  }
+}
+
+template <int KMAX, bool SILU, bool HALF, bool HIN>
+static void launch_warp_one(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
+                            float eps, cudaStream_t st) {
+  const int BG = B * G;
+  groupnorm_warp_kernel<KMAX, SILU, HALF, HIN><<<ceil_div(BG, 8), 256, 0, st>>>(x, y, gamma, beta, BG, HW, C, G, eps);
+}
+
+template <int KMAX>
+static void launch_warp(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
+                        float eps, int silu, int in_f16, int out_f16, cudaStream_t st) {
+  const int sel = (silu ? 4 : 0) | (out_f16 ? 2 : 0) | (in_f16 ? 1 : 0);
+  switch (sel) {
+    case 0: launch_warp_one<KMAX, false, false, false>(x, y, gamma, beta, B, HW, C, G, eps, st); break;
+    case 1: launch_warp_one<KMAX, false, false, true>(x, y, gamma, beta, B, HW, C, G, eps, st); break;
+    case 2: launch_warp_one<KMAX, false, true, false>(x, y, gamma, beta, B, HW, C, G, eps, st); break;
+    case 3: launch_warp_one<KMAX, false, true, true>(x, y, gamma, beta, B, HW, C, G, eps, st); break;
+    case 4: launch_warp_one<KMAX, true, false, false>(x, y, gamma, beta, B, HW, C, G, eps, st); break;
+    case 5: launch_warp_one<KMAX, true, false, true>(x, y, gamma, beta, B, HW, C, G, eps, st); break;
+    case 6: launch_warp_one<KMAX, true, true, false>(x, y, gamma, beta, B, HW, C, G, eps, st); break;
+    default: launch_warp_one<KMAX, true, true, true>(x, y, gamma, beta, B, HW, C, G, eps, st); break;
+  }
+}
+
 static int g_gn_reg = -1;
+static int g_gn_warp = -1;
+
+static int g_gn_stage = -1;
 
 template <bool SILU, bool HALF, bool HIN>
 static void launch_sweep(const void* x, void* y, const float* gamma, const float* beta, int B, int NT, size_t smem,
                          int HW, int C, int G, float eps, cudaStream_t st) {
-  groupnorm_nhwc_kernel<SILU, HALF, HIN><<<B, NT, smem, st>>>(x, y, gamma, beta, HW, C, G, eps);
+  if (g_gn_stage < 0) {
+    const char* e = getenv("CNB_GN_STAGE");
+    g_gn_stage = e ? atoi(e) : 1;
+  }
+  const size_t slab = (size_t)HW * C * 2;                  // fp16 slab
+  const size_t staged = (smem + 127) / 128 * 128 + slab;
+  if (HIN && g_gn_stage && slab % 16 == 0 && slab < (1u << 20) && staged <= 110 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(groupnorm_nhwc_kernel<SILU, HALF, HIN, HIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           110 * 1024);
+      attr_set = true;
+    }
+    groupnorm_nhwc_kernel<SILU, HALF, HIN, HIN><<<B, NT, staged, st>>>(x, y, gamma, beta, HW, C, G, eps);
+  } else {
+    groupnorm_nhwc_kernel<SILU, HALF, HIN, false><<<B, NT, smem, st>>>(x, y, gamma, beta, HW, C, G, eps);
+  }
 }
 
 int groupnorm(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
@@ -370,6 +514,23 @@ int groupnorm(const void* x, void* y, const float* gamma, const float* beta, int
   if (g_gn_reg < 0) {
     const char* e = getenv("CNB_GN_REG");
     g_gn_reg = e ? atoi(e) : 1;
+  }
+  // Warp-per-group kernel: groups of 16 / 32 / 64 / 128 channels whose pixels fit 13 vectors per lane
+  if (g_gn_warp < 0) {
+    const char* e = getenv("CNB_GN_WARP");
+    g_gn_warp = e ? atoi(e) : 1;
+  }
+  {
+    const int cgq = (C / G) / 4;
+    if (g_gn_warp && (C / G) % 4 == 0 && (cgq == 4 || cgq == 8 || cgq == 16 || cgq == 32)) {
+      const int k = ceil_div(HW, 32 / cgq);
+      if (k <= 13) {      // (25 vectors per lane was tried for 128 ch @ 14x14: register pressure makes it lose to the staged kernel)
+        if (k <= 7) launch_warp<7>(x, y, gamma, beta, B, HW, C, G, eps, silu, in_f16, out_f16, st);
+        else launch_warp<13>(x, y, gamma, beta, B, HW, C, G, eps, silu, in_f16, out_f16, st);
+        CNB_LAUNCH_CHECK();
+        return CNB_OK;
+      }
+    }
   }
   // Register-resident kernel when one CTA holds a whole sample (<= 256 threads x 16 float4): measured 1.2-1.6x faster
   // than the three-sweep kernel on the 7x7 / 16-channel slabs.  Splitting a sample over a cluster (CNB_GN_SPLIT=8)

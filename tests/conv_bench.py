@@ -87,8 +87,10 @@ if what in ("gn", "all"):
     for C, hw, G in [(64, 28, 8), (32, 28, 8), (16, 28, 8), (128, 14, 8), (256, 7, 8), (128, 7, 8)]:
         x = torch.randn(B, hw, hw, C, device="cuda")
         g, b = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
-        for f16 in (False, True):
-            ms = timeit(lambda: ops.groupnorm(x, g, b, G, True, out_f16=f16))
-            by = (6.0 if f16 else 8.0) * x.numel()
-            print(f"gn C={C} @{hw} out={'f16' if f16 else 'f32'}: {ms * 1e3:8.1f} us  {by / ms / 1e6:8.1f} GB/s", flush=True)
+        for in16, f16 in ((False, False), (False, True), (True, True)):
+            xi = x.half() if in16 else x
+            ms = timeit(lambda: ops.groupnorm(xi, g, b, G, True, out_f16=f16))
+            by = ((2.0 if in16 else 4.0) + (2.0 if f16 else 4.0)) * x.numel()
+            print(f"gn C={C} @{hw} in={'f16' if in16 else 'f32'} out={'f16' if f16 else 'f32'}: {ms * 1e3:8.1f} us  "
+                  f"{by / ms / 1e6:8.1f} GB/s", flush=True)
 print("flag", rt.lib().cnb_tc_error_flag())

@@ -131,7 +131,8 @@ def test_conv_transpose_into_concat(pk, B, C, H, W, mode, tol):
 
 
 @pytest.mark.parametrize("B,C,G,H,W", [(2, 16, 8, 28, 28), (3, 64, 8, 14, 14), (2, 256, 8, 7, 7), (2, 384, 32, 8, 8),
-                                       (1, 768, 32, 4, 4), (2, 32, 8, 1, 1), (1, 128, 8, 28, 28), (2, 96, 8, 5, 7)])
+                                       (1, 768, 32, 4, 4), (2, 32, 8, 1, 1), (1, 128, 8, 28, 28), (2, 96, 8, 5, 7),
+                                       (3, 64, 8, 28, 28), (2, 128, 32, 32, 32), (300, 32, 8, 28, 28)])
 @pytest.mark.parametrize("silu", [False, True])
 def test_groupnorm(pk, B, C, G, H, W, silu):
     ops, rt = pk
@@ -145,6 +146,14 @@ def test_groupnorm(pk, B, C, G, H, W, silu):
     got16 = ops.groupnorm(nhwc(x).cuda(), g.cuda(), b.cuda(), G, silu, out_f16=True)
     assert got16.dtype == torch.float16
     assert rel_l2(nchw(got16.float().cpu()), want) < 6e-4
+    # fp16 activation stream: fp16 in (statistics in fp32 over the rounded input), fp16 / fp32 out
+    xh = x.half()
+    want_h = F.group_norm(xh.float(), G, g, b, eps=1e-5)
+    if silu:
+        want_h = F.silu(want_h)
+    for o16, tol in ((True, 6e-4), (False, 3e-6)):
+        got = ops.groupnorm(nhwc(xh).cuda(), g.cuda(), b.cuda(), G, silu, out_f16=o16)
+        assert rel_l2(nchw(got.float().cpu()), want_h) < tol
 
 
 @pytest.mark.parametrize("B,L,E,heads", [(2, 784, 64, 4), (2, 784, 16, 4), (3, 196, 128, 4), (2, 49, 256, 4),
