@@ -1,8 +1,7 @@
 // Direct CUDA-core convolutions for the tiny-channel ends of the U-Nets (HBM-bound; judged by GB/s, exact fp32 FFMA):
 //   conv_small_cin  : Cin <= 4  (conv_in with 1/3/4 image channels, first hint conv with 3 channels), Cout % 4 == 0.
-//                     A lane owns 4 output channels (weights [K][Cout] in smem, float4 per k); the Cout/4 lanes of
-//                     a pixel read the same input taps (L1 broadcast) and together write one contiguous
-//                     channels-last row segment, so a warp store is a run of full 128-byte lines.
+//                     A thread owns one output pixel x a block of 32 output channels (accumulators in registers,
+//                     weights [K][32] in smem read as warp-uniform float4 broadcasts).
 //   conv_small_cout : Cout <= 4 (conv_out to 1/3/4 image channels), Cin % 4 == 0.  One thread per output pixel; the
 //                     3x3 neighbourhood is re-read from L1 by the neighbouring threads, weights are warp-uniform
 //                     shared-memory broadcasts.
@@ -18,55 +17,62 @@ struct SmallArgs {
   int M, K;
 };
 
-__global__ void __launch_bounds__(256)
+// One thread = one output pixel x one block of COB output channels: the taps are loaded once and reused for all COB
+// channels (weights are warp-uniform float4 broadcasts from smem), i.e. ~1.3 instructions per output value instead
+// of the ~75 of a 4-channels-per-thread mapping, which made the first version of this kernel issue-bound at 160 us for
+// conv_in (1 -> 32 @ 28x28, B = 1024) against a 20 us HBM time.
+template <int COB>
+__global__ void __launch_bounds__(128)
 conv_small_cin_kernel(const __grid_constant__ SmallArgs a) {
   const cnb_conv_params& p = a.p;
   const int K = a.K;                       // ntaps * Cin
-  const int lpr = p.Cout >> 2;             // lanes per pixel
-  const int ppb = blockDim.x / lpr;        // pixels per CTA iteration
-  const int lane_c = threadIdx.x % lpr;
-  const int lane_p = threadIdx.x / lpr;
-  const int n = lane_c * 4;
+  const int n0 = blockIdx.y * COB;
   const float* in = reinterpret_cast<const float*>(p.in);
-  extern __shared__ float wsm[];           // [K][Cout]: a lane reads the float4 of its 4 channels, pixels broadcast
-  for (int i = threadIdx.x; i < K * p.Cout; i += blockDim.x) {
-    const int k = i / p.Cout, o = i - k * p.Cout;
-    wsm[i] = __ldg(p.weight + (size_t)o * K + k);
+  extern __shared__ __align__(16) float wsm[];   // [K][COB]
+  for (int i = threadIdx.x; i < K * COB; i += blockDim.x) {
+    const int k = i / COB, o = i - k * COB;
+    wsm[i] = __ldg(p.weight + (size_t)(n0 + o) * K + k);
   }
   __syncthreads();
-  const float4* w4 = reinterpret_cast<const float4*>(wsm) + lane_c;
-
-  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-  if (p.temb && !p.temb_per_sample) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(p.temb + n));
-    bv.x += t.x; bv.y += t.y; bv.z += t.z; bv.w += t.w;
-  }
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= a.M) return;
   const int OHW = p.OH * p.OW;
+  const int b = m / OHW;
+  const int rem = m - b * OHW;
+  const int oy = rem / p.OW;
+  const int ox = rem - oy * p.OW;
+  const int iy0 = oy * p.stride, ix0 = ox * p.stride;
   const int Cin = p.Cin;
-  for (int m = blockIdx.x * ppb + lane_p; m < a.M; m += gridDim.x * ppb) {
-    const int b = m / OHW;
-    const int rem = m - b * OHW;
-    const int oy = rem / p.OW;
-    const int ox = rem - oy * p.OW;
-    const int iy0 = oy * p.stride, ix0 = ox * p.stride;
-    float4 acc = bv;
-    for (int tap = 0; tap < p.ntaps; ++tap) {
-      const int iy = iy0 + p.dy[tap], ix = ix0 + p.dx[tap];
-      if ((unsigned)iy >= (unsigned)p.H || (unsigned)ix >= (unsigned)p.W) continue;
-      const float* src = in + ((size_t)(b * p.H + iy) * p.W + ix) * p.ldi + p.in_coff;
-      const float4* wt = w4 + (size_t)tap * Cin * lpr;
-      for (int c = 0; c < Cin; ++c) {
-        const float x = __ldg(src + c);
-        const float4 wk = wt[(size_t)c * lpr];
-        acc.x = fmaf(x, wk.x, acc.x); acc.y = fmaf(x, wk.y, acc.y);
-        acc.z = fmaf(x, wk.z, acc.z); acc.w = fmaf(x, wk.w, acc.w);
+  float acc[COB];
+#pragma unroll
+  for (int j = 0; j < COB; ++j) acc[j] = 0.f;
+  for (int tap = 0; tap < p.ntaps; ++tap) {
+    const int iy = iy0 + p.dy[tap], ix = ix0 + p.dx[tap];
+    if ((unsigned)iy >= (unsigned)p.H || (unsigned)ix >= (unsigned)p.W) continue;
+    const float* src = in + ((size_t)(b * p.H + iy) * p.W + ix) * p.ldi + p.in_coff;
+    const float4* wt = reinterpret_cast<const float4*>(wsm + (size_t)tap * Cin * COB);
+    for (int c = 0; c < Cin; ++c) {
+      const float x = __ldg(src + c);
+#pragma unroll
+      for (int j = 0; j < COB / 4; ++j) {
+        const float4 w = wt[c * (COB / 4) + j];
+        acc[4 * j + 0] = fmaf(x, w.x, acc[4 * j + 0]); acc[4 * j + 1] = fmaf(x, w.y, acc[4 * j + 1]);
+        acc[4 * j + 2] = fmaf(x, w.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(x, w.w, acc[4 * j + 3]);
       }
     }
-    const size_t pix = ((size_t)b * p.OHf + (oy * p.oy_mul + p.oy_add)) * p.OWf + (ox * p.ox_mul + p.ox_add);
-    if (p.temb && p.temb_per_sample) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(p.temb + (size_t)b * p.temb_ld + n));
-      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+  }
+  const size_t pix = ((size_t)b * p.OHf + (oy * p.oy_mul + p.oy_add)) * p.OWf + (ox * p.ox_mul + p.ox_add);
+#pragma unroll
+  for (int j = 0; j < COB / 4; ++j) {
+    const int n = n0 + 4 * j;
+    float4 o = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+    if (p.bias) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+      o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+    }
+    if (p.temb) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p.temb + (size_t)(p.temb_per_sample ? b : 0) * p.temb_ld + n));
+      o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
     }
     if (p.residual) {
       float4 t;
@@ -80,15 +86,15 @@ conv_small_cin_kernel(const __grid_constant__ SmallArgs a) {
         t = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + pix * p.ldr +
                                                   p.res_coff + n));
       }
-      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
     }
-    if (p.act == 1) { acc.x = silu_f(acc.x); acc.y = silu_f(acc.y); acc.z = silu_f(acc.z); acc.w = silu_f(acc.w); }
+    if (p.act == 1) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
     if (p.out_dtype == 1) {
-      const __half2 lo = __floats2half2_rn(acc.x, acc.y), hi = __floats2half2_rn(acc.z, acc.w);
+      const __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
       *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + pix * p.ldo + p.out_coff + n) =
           make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
     } else {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldo + p.out_coff + n) = acc;
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix * p.ldo + p.out_coff + n) = o;
     }
   }
 }
@@ -153,8 +159,8 @@ conv_small_cout_kernel(const __grid_constant__ SmallArgs a) {
 
 static bool small_cin_ok(const cnb_conv_params* p) {
   const int K = p->ntaps * p->Cin;
-  return p->Cin <= 4 && p->in_dtype == 0 && p->Cout % 4 == 0 && p->Cout >= 4 && p->Cout <= 256 && K <= 64 &&
-         256 % (p->Cout / 4) == 0 && p->ldo % 4 == 0 && p->out_coff % 4 == 0 &&
+  return p->Cin <= 4 && p->in_dtype == 0 && p->Cout % 4 == 0 && p->Cout >= 4 && K <= 64 &&
+         (p->Cout % 32 == 0 || p->Cout == 16 || p->Cout == 8 || p->Cout == 4) && p->ldo % 4 == 0 && p->out_coff % 4 == 0 &&
          (!p->residual || (p->ldr % 4 == 0 && p->res_coff % 4 == 0)) && (!p->temb || p->temb_ld % 4 == 0) &&
          (((uintptr_t)p->out | (uintptr_t)p->bias | (uintptr_t)p->temb | (uintptr_t)p->residual) & 15) == 0;
 }
@@ -173,10 +179,15 @@ int conv2d_small(const cnb_conv_params* p, cudaStream_t st) {
   a.M = p->B * p->OH * p->OW;
   a.K = p->ntaps * p->Cin;
   if (small_cin_ok(p)) {
-    const int ppb = 256 / (p->Cout / 4);
-    int grid = ceil_div(a.M, ppb);
-    if (grid > 148 * 8) grid = 148 * 8;           // grid-stride: the weight matrix is staged in smem once per CTA
-    conv_small_cin_kernel<<<grid, 256, (size_t)a.K * p->Cout * sizeof(float), st>>>(a);
+    const int gx = ceil_div(a.M, 128);
+    if (p->Cout % 32 == 0)
+      conv_small_cin_kernel<32><<<dim3(gx, p->Cout / 32), 128, (size_t)a.K * 32 * sizeof(float), st>>>(a);
+    else if (p->Cout == 16)
+      conv_small_cin_kernel<16><<<dim3(gx, 1), 128, (size_t)a.K * 16 * sizeof(float), st>>>(a);
+    else if (p->Cout == 8)
+      conv_small_cin_kernel<8><<<dim3(gx, 1), 128, (size_t)a.K * 8 * sizeof(float), st>>>(a);
+    else
+      conv_small_cin_kernel<4><<<dim3(gx, 1), 128, (size_t)a.K * 4 * sizeof(float), st>>>(a);
     CNB_LAUNCH_CHECK();
     return CNB_OK;
   }
