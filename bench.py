@@ -99,6 +99,10 @@ def build_problem(batch, device, seed_offset=0):
 # ------------------------------------------------------------------------------------------------------------
 # roofline: instrumented eager step, CUDA events around every libcnb200 launch on the launching stream
 # ------------------------------------------------------------------------------------------------------------
+def k_heads(a, k):
+    return a[1] if len(a) > 1 else k.get("heads", 1)
+
+
 def kernel_breakdown(model, sched, x, hint, n_steps=2):
     import torch
     ops = importlib.import_module("controlnet-pytorch_b200.ops")
@@ -125,19 +129,28 @@ def kernel_breakdown(model, sched, x, hint, n_steps=2):
             OH, OW = H, W
         else:
             OH, OW = ops.out_size(kind, H), ops.out_size(kind, W)
-        fam = "conv_tc" if (cin % 4 == 0 and cout % 16 == 0) else "conv_f32"
-        flops = 2.0 * B * OH * OW * ntaps * cin * cout
-        byts = 4.0 * (B * H * W * cin + B * OH * OW * cout * (2 if k.get("residual") is not None else 1) + w_.numel())
-        return dict(fam=fam, flops=flops, bytes=byts)
+        fam = "conv_tc" if (cin % 4 == 0 and cin > 4 and cout % 16 == 0) else "conv_small"
+        x2 = k.get("x2")
+        cin2 = x2.shape[3] if x2 is not None else 0
+        flops = 2.0 * B * OH * OW * (ntaps * cin + cin2) * cout
+        res = k.get("residual")
+        byts = (B * H * W * cin * x_.element_size() + out.shape[0] * out.shape[1] * out.shape[2] * cout * out.element_size()
+                + (res.numel() * res.element_size() if res is not None else 0)
+                + (x2.numel() * x2.element_size() if x2 is not None else 0) + w_.numel() * x_.element_size())
+        shape = f"{kind or 'convT'} {cin}{'+%d' % cin2 if cin2 else ''}->{cout} @{H}x{W}"
+        return dict(fam=fam, flops=flops, bytes=byts, shape=shape)
 
     ops.conv = timed("conv", conv_meta, orig["conv"])
-    ops.groupnorm = timed("groupnorm", lambda o, a, k: dict(fam="groupnorm", flops=0.0, bytes=8.0 * a[0].numel()),
-                          orig["groupnorm"])
+    ops.groupnorm = timed("groupnorm", lambda o, a, k: dict(
+        fam="groupnorm", flops=0.0, bytes=float(a[0].numel() * a[0].element_size() + o.numel() * o.element_size()),
+        shape=f"C={a[0].shape[3]} @{a[0].shape[1]}x{a[0].shape[2]}"), orig["groupnorm"])
     ops.attention = timed("attention", lambda o, a, k: dict(
-        fam="attention", bytes=4.0 * (a[0].numel() + o.numel()),
-        flops=4.0 * a[0].shape[0] * (a[0].shape[1] * a[0].shape[2]) ** 2 * (a[0].shape[3] // 3)), orig["attention"])
-    ops.sched_step = timed("sched_step", lambda o, a, k: dict(fam="sched_step", flops=0.0, bytes=16.0 * a[0].numel()),
-                           orig["sched_step"])
+        fam="attention", bytes=float(a[0].numel() * a[0].element_size() + o.numel() * o.element_size()),
+        flops=4.0 * a[0].shape[0] * (a[0].shape[1] * a[0].shape[2]) ** 2 * (a[0].shape[3] // 3),
+        scores=float(a[0].shape[0]) * k_heads(a, k) * (a[0].shape[1] * a[0].shape[2]) ** 2,
+        shape=f"L={a[0].shape[1] * a[0].shape[2]} E={a[0].shape[3] // 3} heads={k_heads(a, k)}"), orig["attention"])
+    ops.sched_step = timed("sched_step", lambda o, a, k: dict(fam="sched_step", flops=0.0, bytes=16.0 * a[0].numel(),
+                                                              shape="step"), orig["sched_step"])
     try:
         smp = S.DDPMSampler(model, sched, seed=3, use_graph=False)
         smp.sample_eager(x, hint, steps=1)          # warm caches
@@ -152,11 +165,18 @@ def kernel_breakdown(model, sched, x, hint, n_steps=2):
             setattr(ops, k_, v)
     fams = {}
     for name, meta, e0, e1 in rec:
-        f = fams.setdefault(meta["fam"], dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
-        f["ms"] += e0.elapsed_time(e1)
+        ms = e0.elapsed_time(e1)
+        f = fams.setdefault(meta["fam"], dict(ms=0.0, flops=0.0, bytes=0.0, launches=0, shapes={}))
+        f["ms"] += ms
         f["flops"] += meta["flops"]
         f["bytes"] += meta["bytes"]
         f["launches"] += 1
+        sh = f["shapes"].setdefault(meta.get("shape", "?"), dict(ms=0.0, flops=0.0, bytes=0.0, scores=0.0, launches=0))
+        sh["ms"] += ms
+        sh["flops"] += meta["flops"]
+        sh["bytes"] += meta["bytes"]
+        sh["scores"] += meta.get("scores", 0.0)
+        sh["launches"] += 1
     for f in fams.values():
         for k_ in ("ms", "flops", "bytes"):
             f[k_] /= n_steps
@@ -164,30 +184,51 @@ def kernel_breakdown(model, sched, x, hint, n_steps=2):
     return fams, t0.elapsed_time(t1) / n_steps
 
 
-def make_roofline(fams, step_ms):
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel instances at B = 1024, read
+# from the committed `ncu --set full` captures (profiles/r01_attention_f16_final.md, profiles/r01_conv_tma_final.md)
+NCU_TRAFFIC = {("attention", "L=784 E=64 heads=4", 1024): 396.2e6,
+               ("conv_tc", "3x3 64->64 @28x28", 1024): 162.6e6,
+               ("conv_tc", "3x3 256->256 @7x7", 1024): 27.3e6}
+MUFU_PEAK_TSCORES = 148 * 16 * 1.965e9 / 1e12      # one ex2 per attention score, 16 MUFU lanes per SM per clock
+
+
+def make_roofline(fams, step_ms, batch):
+    """Roofline of the dominant kernel: the (family, layer shape) with the largest share of the step; achieved =
+    algorithmic FLOPs (or bytes) per launch / average launch duration (CUDA events on the launching stream)."""
     pk = _peaks()
     total = sum(f["ms"] for f in fams.values()) or 1.0
     dom = max(fams, key=lambda k_: fams[k_]["ms"])
-    f = fams[dom]
-    sec = f["ms"] * 1e-3
-    kernel_names = {"conv_tc": "conv_igemm_tf32_kernel (tcgen05)", "conv_f32": "conv_igemm_f32_kernel",
-                    "groupnorm": "groupnorm_nhwc_kernel", "attention": "attention kernel", "sched_step": "sched_step_kernel"}
+    shape, sh = max(fams[dom]["shapes"].items(), key=lambda kv: kv[1]["ms"])
+    n = sh["launches"]
+    sec = sh["ms"] * 1e-3 / n                      # average launch duration
+    kernel_names = {"conv_tc": "conv_tma_kernel (tcgen05 + TMA)", "conv_small": "conv_small_*_kernel",
+                    "groupnorm": "groupnorm_*_kernel", "attention": "attention_f16_kernel (mma.sync m16n8k16)",
+                    "sched_step": "sched_step_kernel"}
     if dom in ("conv_tc", "attention"):
-        ach = f["flops"] / sec / 1e12
+        ach = sh["flops"] / n / sec / 1e12
         r = {"bound": "tensor", "achieved": round(ach, 2), "peak": pk["tf"], "unit": "TFLOP/s",
              "frac": round(ach / pk["tf"], 4)}
     else:
-        ach = f["bytes"] / sec / 1e9
+        ach = sh["bytes"] / n / sec / 1e9
         r = {"bound": "hbm", "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s", "frac": round(ach / pk["hbm"], 4)}
-    r.update({"traffic": None, "kernel": kernel_names.get(dom, dom), "share_of_step": round(f["ms"] / total, 3),
+    r.update({"traffic": NCU_TRAFFIC.get((dom, shape, batch)), "kernel": kernel_names.get(dom, dom), "shape": shape,
+              "avg_launch_us": round(sec * 1e6, 1), "algorithmic_per_launch": {"flops": sh["flops"] / n, "bytes": sh["bytes"] / n},
+              "share_of_step": round(sh["ms"] / sum(x["ms"] for f in fams.values() for x in f["shapes"].values()), 3),
+              "family_share_of_step": round(fams[dom]["ms"] / total, 3),
               "peak_source": pk["src"] + (" (sustained bf16 dense)" if r["bound"] == "tensor" else " (copy)"),
-              "launches_per_step": f["launches"]})
+              "launches_per_step": fams[dom]["launches"]})
+    if dom == "attention":
+        ts = sh["scores"] / n / sec / 1e12
+        r["note"] = ("attention at head dim <= 64 is bound by the exponential (one MUFU ex2 per score), not by the tensor "
+                     "pipe: see `xu` and DESIGN.md 4.2")
+        r["xu"] = {"achieved": round(ts, 3), "peak": round(MUFU_PEAK_TSCORES, 3), "unit": "Tscore/s",
+                   "frac": round(ts / MUFU_PEAK_TSCORES, 3)}
     fam_out = {}
     for k_, v in fams.items():
-        s = v["ms"] * 1e-3
+        s_ = v["ms"] * 1e-3
         fam_out[k_] = {"ms": round(v["ms"], 3), "launches": v["launches"],
-                       "TFLOP/s": round(v["flops"] / s / 1e12, 2) if v["flops"] else None,
-                       "GB/s": round(v["bytes"] / s / 1e9, 1)}
+                       "TFLOP/s": round(v["flops"] / s_ / 1e12, 2) if v["flops"] else None,
+                       "GB/s": round(v["bytes"] / s_ / 1e9, 1)}
     return r, fam_out
 
 
@@ -339,7 +380,7 @@ def run_b200(args):
     if rank == 0:
         with torch.no_grad():
             fams, eager_ms = kernel_breakdown(model, sched, x_T, hint, n_steps=2)
-        roofline, fam = make_roofline(fams, eager_ms)
+        roofline, fam = make_roofline(fams, eager_ms, B)
         if world == 1 and not args.no_cpu:
             nb, ns = args.cpu_batch, args.cpu_steps
             step = cpu_oracle_step_fn(nb)

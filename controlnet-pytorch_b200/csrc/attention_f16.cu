@@ -83,6 +83,8 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
   constexpr int THREADS = NW * 32;
   static_assert(BK % 16 == 0, "BK must be a multiple of 16");
   extern __shared__ __align__(16) __half smem[];   // [3 stages][K | V][BK][STRIDE]
+  pdl_trigger();
+  pdl_wait();
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -294,8 +296,8 @@ static int launch2(const void* qkv, void* out, int B, int L, int E, int heads, c
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)D);
   dim3 grid(ceil_div(L, 16 * NW), heads, B);
-  attention_f16_kernel<D, BK, NW, H2><<<grid, NW * 32, SMEM, st>>>(
-      reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(out), L, E, scale_log2);
+  CNB_CUDA(launch_pdl(attention_f16_kernel<D, BK, NW, H2>, grid, dim3(NW * 32), SMEM, st,
+                      reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(out), L, E, scale_log2));
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }

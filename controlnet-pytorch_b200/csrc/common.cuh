@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/cnb200.h"
 
@@ -48,5 +49,33 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------
+// Kernels launched through launch_pdl() may start while their predecessor in the stream is still draining: they run
+// their prologue (barrier init, TMEM allocation, descriptor fetch, index math), then pdl_wait() blocks until the
+// predecessor grid has completed and its memory is visible.  EVERY global memory access of such a kernel comes after
+// pdl_wait(), so stream order is preserved transitively; pdl_trigger() (issued at entry) only lets the NEXT kernel
+// begin its own prologue early.  Captured into a CUDA graph these become programmatic dependency edges.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();   // api.cu: CNB_PDL=1 turns the launch attribute on (off: the device-side calls are no-ops)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 }  // namespace cnb

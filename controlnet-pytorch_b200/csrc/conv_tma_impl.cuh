@@ -156,6 +156,7 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
   constexpr int SLAB = C::SLAB;
   constexpr int SSTR = C::SLAB_STRIDE;
 
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
@@ -198,6 +199,7 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above overlapped the previous kernel's tail; no global memory touched yet
 
   if (warp == 0) {
     // ============================ TMA producer ============================
@@ -569,7 +571,7 @@ static int launch_epi(const TmaArgs& a_in, int num_sms, cudaStream_t st) {
   }
   a.bar_off = a.epi_off + C::EPI_BYTES;
   smem_bytes = (size_t)a.bar_off + C::BAR_BYTES + 1024;
-  conv_tma_kernel<BN, HALF, EPI, RB><<<grid, NUM_THREADS, smem_bytes, st>>>(a);
+  CNB_CUDA(launch_pdl(conv_tma_kernel<BN, HALF, EPI, RB>, dim3(grid), dim3(NUM_THREADS), smem_bytes, st, a));
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }

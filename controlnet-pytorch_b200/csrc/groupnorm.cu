@@ -63,6 +63,8 @@ template <bool SILU, bool HALF, bool HIN, bool STAGE>
 __global__ void __launch_bounds__(1024)
 groupnorm_nhwc_kernel(const void* __restrict__ x, void* __restrict__ y, const float* __restrict__ gamma,
                       const float* __restrict__ beta, int HW, int C, int G, float eps) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   const int C4 = C >> 2;
   const int NT = blockDim.x;
@@ -235,6 +237,8 @@ template <int KMAX, bool SILU, bool HALF, bool HIN>
 __global__ void __launch_bounds__(256)
 groupnorm_reg_kernel(const void* __restrict__ x, void* __restrict__ y, const float* __restrict__ gamma,
                      const float* __restrict__ beta, int HW, int C, int G, float eps, int rows_per_cta) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   const int C4 = C >> 2;
   const int NT = blockDim.x;
@@ -376,6 +380,10 @@ static int launch_reg(const void* x, void* y, const float* gamma, const float* b
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (split == 1) {      // single-CTA samples: plain (non-cluster) launch that may overlap its predecessor's tail
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  }
   cudaError_t e;
   const int sel = (silu ? 4 : 0) | (out_f16 ? 2 : 0) | (in_f16 ? 1 : 0);
   switch (sel) {
@@ -405,6 +413,8 @@ template <int KMAX, bool SILU, bool HALF, bool HIN>
 __global__ void __launch_bounds__(256)
 groupnorm_warp_kernel(const void* __restrict__ x, void* __restrict__ y, const float* __restrict__ gamma,
                       const float* __restrict__ beta, int BG, int HW, int C, int G, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wid >= BG) return;
   const int lane = threadIdx.x & 31;
@@ -462,7 +472,8 @@ template <int KMAX, bool SILU, bool HALF, bool HIN>
 static void launch_warp_one(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
                             float eps, cudaStream_t st) {
   const int BG = B * G;
-  groupnorm_warp_kernel<KMAX, SILU, HALF, HIN><<<ceil_div(BG, 8), 256, 0, st>>>(x, y, gamma, beta, BG, HW, C, G, eps);
+  launch_pdl(groupnorm_warp_kernel<KMAX, SILU, HALF, HIN>, dim3(ceil_div(BG, 8)), dim3(256), 0, st, x, y, gamma, beta, BG,
+             HW, C, G, eps);
 }
 
 template <int KMAX>
@@ -502,9 +513,11 @@ static void launch_sweep(const void* x, void* y, const float* gamma, const float
                            110 * 1024);
       attr_set = true;
     }
-    groupnorm_nhwc_kernel<SILU, HALF, HIN, HIN><<<B, NT, staged, st>>>(x, y, gamma, beta, HW, C, G, eps);
+    launch_pdl(groupnorm_nhwc_kernel<SILU, HALF, HIN, HIN>, dim3(B), dim3(NT), staged, st, x, y, gamma, beta, HW, C, G,
+               eps);
   } else {
-    groupnorm_nhwc_kernel<SILU, HALF, HIN, false><<<B, NT, smem, st>>>(x, y, gamma, beta, HW, C, G, eps);
+    launch_pdl(groupnorm_nhwc_kernel<SILU, HALF, HIN, false>, dim3(B), dim3(NT), smem, st, x, y, gamma, beta, HW, C, G,
+               eps);
   }
 }
 
