@@ -60,9 +60,6 @@ struct alignas(64) TmaArgs {
   uint32_t tap_off[CNB_MAX_TAPS];   // offset_w | offset_h << 16
 };
 
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const void* map, uint64_t* bar, int c, int w, int h,
                                                    int n, uint16_t off_w, uint16_t off_h) {
   asm volatile(
@@ -79,41 +76,11 @@ __device__ __forceinline__ void tma_load_tiled_4d(uint32_t dst, const void* map,
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* map, uint64_t* bar, int x, int y) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-      "[%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
 __device__ __forceinline__ float4 ld_half4(const __half* p) {
   const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
   const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
   const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
   return make_float4(lo.x, lo.y, hi.x, hi.y);
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major shared-memory matrix descriptor for a tile whose rows are RB bytes = one swizzle span
-// (cute::UMMA::SmemDescriptor): start >> 4 | LBO (unused) | SBO = 8 rows | version 1 | layout 2 / 4 / 6.
-template <int RB>
-__device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t smem_addr) {
-  static_assert(RB == 128 || RB == 64 || RB == 32, "row bytes = swizzle span");
-  constexpr uint64_t layout = RB == 128 ? 2 : (RB == 64 ? 4 : 6);
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)((8 * RB) >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= layout << 61;
-  return d;
 }
 
 constexpr int pow2_at_least(int v, int p = 32) { return p >= v ? p : pow2_at_least(v, p * 2); }

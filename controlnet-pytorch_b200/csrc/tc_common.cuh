@@ -22,6 +22,10 @@ static inline int tc_read_clear_error() {
 namespace tc {
 
 constexpr long long WAIT_LIMIT_CYCLES = 4000000000ll;   // ~2 s at 1.9 GHz
+// Suspend-time hint of the parked try_wait.  Measured on B200 (tests/probes/lat_probe.cu): without a hint a failing try_wait
+// returns after ~6 cycles, so a waiting warp spins through ~135 probes per 1000 cycles and steals issue slots from
+// the warps that do the work; with a hint >= 10 us the warp is parked and still wakes ~160 cycles after the arrival.
+constexpr uint32_t TRY_WAIT_SUSPEND_NS = 20000u;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -42,7 +46,20 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
-// Bounded wait.  Returns false (and latches *abort) if the phase did not complete within the guard.
+// try_wait with a suspend-time hint: the warp is parked instead of re-probing (see TRY_WAIT_SUSPEND_NS)
+__device__ __forceinline__ uint32_t mbar_try_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(TRY_WAIT_SUSPEND_NS)
+      : "memory");
+  return ok;
+}
+// Bounded wait.  Returns false (and latches *abort) if the phase did not complete within the guard.  Spinning
+// variant: lowest wake-up latency, right for kernels with few warps per SM (the convolution pipelines).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile int* abort) {
   if (mbar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
@@ -55,6 +72,26 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volati
       return false;
     }
   }
+}
+// Parked variant for kernels with many waiting warps per SM sub-partition (attention_tc05): the first probe is
+// inline, the guard loop lives out of line and every probe parks the warp.
+static __device__ __noinline__ bool mbar_wait_parked_slow(uint64_t* bar, uint32_t parity, volatile int* abort) {
+  const long long t0 = clock64();
+  while (true) {
+#pragma unroll 1
+    for (int spin = 0; spin < 64; ++spin)
+      if (mbar_try_wait_parked(bar, parity)) return true;
+    if (*abort) return false;
+    if (clock64() - t0 > WAIT_LIMIT_CYCLES) {
+      *abort = 1;
+      atomicExch(&g_tc_error, 1);
+      return false;
+    }
+  }
+}
+__device__ __forceinline__ bool mbar_wait_parked(uint64_t* bar, uint32_t parity, volatile int* abort) {
+  if (mbar_try_wait_parked(bar, parity)) return true;
+  return mbar_wait_parked_slow(bar, parity, abort);
 }
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
@@ -129,6 +166,41 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool half) {
   uint32_t fmt = half ? 0u : 2u;   // F16F32Format: F16 = 0, BF16 = 1, TF32 = 2
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- TMA / TMEM helpers shared by the TMA-fed kernels ----
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* map, uint64_t* bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor for a tile whose rows are RB bytes = one swizzle span
+// (cute::UMMA::SmemDescriptor): start >> 4 | LBO (unused) | SBO = 8 rows | version 1 | layout 2 / 4 / 6.
+template <int RB>
+__device__ __forceinline__ uint64_t make_desc_kmajor(uint32_t smem_addr) {
+  static_assert(RB == 128 || RB == 64 || RB == 32, "row bytes = swizzle span");
+  constexpr uint64_t layout = RB == 128 ? 2 : (RB == 64 ? 4 : 6);
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * RB) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
 }
 
 }  // namespace tc

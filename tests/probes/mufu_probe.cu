@@ -1,0 +1,62 @@
+// Does a stream of MUFU.EX2 from one warp starve the other warps of the same SM sub-partition?
+// Block = 8 warps (2 per SMSP: warps w and w+4 share SMSP w%4).  Warps 0..3 run kind A, warps 4..7 run kind B.
+#include <cstdio>
+#include <cuda_runtime.h>
+__device__ __forceinline__ float ex2f(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// kind: 0 = idle, 1 = independent MUFU x N, 2 = independent FFMA x N, 3 = dependent FFMA chain, 4 = mixed FFMA+MUFU+pack like softmax
+__device__ float run_kind(int kind, int iters, float seed) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = seed + i * 0.001f;
+  if (kind == 1) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = ex2f(a[i]);
+    }
+  } else if (kind == 2) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(0.999f), "f"(0.001f));
+    }
+  } else if (kind == 3) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[0]) : "f"(0.999f), "f"(0.001f));
+    }
+  } else if (kind == 4) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(0.999f), "f"(-0.001f));
+        a[i] = ex2f(a[i]);
+      }
+    }
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  return s;
+}
+__global__ void probe(int kindA, int kindB, int iters, long long* out, float* sink) {
+  const int warp = threadIdx.x >> 5;
+  const int kind = warp < 4 ? kindA : kindB;
+  __syncthreads();
+  const long long t0 = clock64();
+  float s = run_kind(kind, iters, threadIdx.x * 1e-3f);
+  const long long t1 = clock64();
+  if ((threadIdx.x & 31) == 0) out[warp] = t1 - t0;
+  sink[threadIdx.x] = s;
+}
+int main() {
+  long long* d; float* sink; cudaMalloc(&d, 64); cudaMalloc(&sink, 4096);
+  const int iters = 256;   // x16 instructions
+  const char* nm[5] = {"idle", "MUFU", "FFMA-indep", "FFMA-chain", "FFMA+MUFU"};
+  for (int ka : {0, 1, 4}) for (int kb : {0, 1, 2, 3, 4}) {
+    probe<<<1, 256>>>(ka, kb, iters, d, sink);
+    cudaDeviceSynchronize();
+    long long h[8]; cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
+    printf("A=%-10s B=%-10s  A: %6.2f cyc/instr   B: %6.2f cyc/instr\n", nm[ka], nm[kb], h[0] / (double)(iters * 16) / (ka == 4 ? 2 : 1),
+           h[4] / (double)(iters * 16) / (kb == 4 ? 2 : 1));
+  }
+  return 0;
+}

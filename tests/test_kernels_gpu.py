@@ -188,6 +188,45 @@ def test_attention_f16(pk, B, L, E, heads):
     assert rel_l2(got.float().cpu().reshape(B, L, E), want) < 1.5e-3
 
 
+@pytest.mark.parametrize("B,L,E,heads", [(2, 784, 64, 4), (3, 196, 128, 4), (2, 1024, 128, 8), (3, 130, 64, 4), (1, 96, 64, 4),
+                                         (2, 128, 32, 2), (1, 129, 64, 2), (5, 257, 256, 16), (2, 1024, 512, 16)])
+def test_attention_tc05(pk, B, L, E, heads):
+    """tcgen05 / TMEM flash attention (S and P V as tcgen05.mma tiles, split-K online softmax with lazy rescale, V
+    transposed in smem, denominators on the tensor core) against exact softmax attention on the same fp16 q|k|v."""
+    ops, rt = pk
+    qkv = rnd(B, L, 3 * E, seed=5).half()
+    d = E // heads
+    q, k, v = [t.float().reshape(B, L, heads, d).transpose(1, 2) for t in qkv.split(E, dim=-1)]
+    want = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), -1) @ v).transpose(1, 2).reshape(B, L, E)
+    got = ops.attention(qkv.reshape(B, L, 1, 3 * E).cuda(), heads, tc05=True)
+    assert got.dtype == torch.float16
+    assert rel_l2(got.float().cpu().reshape(B, L, E), want) < 1.5e-3
+    assert rt.lib().cnb_tc_error_flag() == 0
+
+
+@pytest.mark.parametrize("B,L,E,heads", [(2, 784, 64, 4), (2, 300, 128, 4), (1, 1024, 256, 16), (2, 97, 64, 4)])
+@pytest.mark.parametrize("gain", [4.0, 12.0])
+@pytest.mark.parametrize("tc05", [False, True])
+def test_attention_f16_growing_scores(pk, B, L, E, heads, gain, tc05):
+    """Scores whose row maximum keeps growing along the key axis (keys scaled by a ramp): the running maximum of an
+    online softmax has to move many times, which exercises the lazy O-rescale path of the tcgen05 kernel (reference
+    maximum only moves past a 2^8 headroom) and the peaked-softmax regime (P underflow of the early keys)."""
+    ops, rt = pk
+    d = E // heads
+    qkv = rnd(B, L, 3 * E, seed=3)
+    ramp = torch.linspace(0.05, 1.0, L).reshape(1, L, 1)
+    q, k, v = qkv.split(E, dim=-1)
+    q = torch.sign(q) * (0.5 + q.abs()) * math.sqrt(gain)          # no tiny queries: every row sees the ramp
+    k = torch.sign(k) * (0.5 + k.abs()) * ramp * math.sqrt(gain)
+    qkv = torch.cat([q, k, v], dim=-1).half()
+    q, k, v = [t.float().reshape(B, L, heads, d).transpose(1, 2) for t in qkv.split(E, dim=-1)]
+    want = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), -1) @ v).transpose(1, 2).reshape(B, L, E)
+    got = ops.attention(qkv.reshape(B, L, 1, 3 * E).cuda(), heads, tc05=tc05)
+    assert torch.isfinite(got).all()
+    assert rel_l2(got.float().cpu().reshape(B, L, E), want) < 2e-3
+    assert rt.lib().cnb_tc_error_flag() == 0
+
+
 @pytest.mark.parametrize("B,C,Cx,Cout,H,W", [(3, 64, 64, 64, 14, 14), (2, 64, 32, 64, 28, 28), (5, 128, 256, 128, 7, 7),
                                              (2, 16, 64, 16, 9, 11), (33, 32, 32, 32, 14, 14), (76, 64, 32, 64, 28, 28)])
 def test_conv_k_concat_second_input(pk, B, C, Cx, Cout, H, W):
