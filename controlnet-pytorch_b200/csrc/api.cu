@@ -37,6 +37,10 @@ int conv2d_small(const cnb_conv_params* p, cudaStream_t st);
 bool conv2d_small_supported(const cnb_conv_params* p);
 int conv2d_tma(const cnb_conv_params* p, cudaStream_t st);
 bool conv2d_tma_supported(const cnb_conv_params* p);
+bool groupnorm_big_eligible(int B, int HW, int C, int G, int in_f16);
+size_t groupnorm_big_workspace(int B, int HW, int C, int G);
+int groupnorm_big(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G, float eps,
+                  int silu, int out_f16, void* workspace, size_t ws_bytes, cudaStream_t st);
 int groupnorm(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
               float eps, int silu, int in_f16, int out_f16, cudaStream_t st);
 int attention_f32(const float* qkv, float* out, int B, int L, int E, int heads, cudaStream_t st);
@@ -112,6 +116,20 @@ extern "C" int cnb_conv2d(const cnb_conv_params* p, cnb_stream_t stream) {
   CNB_REQUIRE(p->out_dtype == 0 && p->res_dtype == 0, "conv2d: fp16 output / residual needs a tensor-core eligible layer");
   CNB_REQUIRE(p->in_dtype == 0, "conv2d: fp16 activations need a tensor-core eligible layer (Cin %% 8 == 0, Cout %% 16 == 0)");
   return conv2d_f32(p, st);
+}
+
+extern "C" size_t cnb_groupnorm_workspace_bytes(int B, int HW, int C, int G, int in_f16) {
+  if (B <= 0 || HW <= 0 || C <= 0 || G <= 0 || !groupnorm_big_eligible(B, HW, C, G, in_f16)) return 0;
+  return groupnorm_big_workspace(B, HW, C, G);
+}
+
+extern "C" int cnb_groupnorm_ws(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C,
+                                int G, float eps, int silu, int in_f16, int out_f16, void* workspace, size_t ws_bytes,
+                                cnb_stream_t stream) {
+  CNB_REQUIRE(x && y && gamma && beta && B > 0 && HW > 0 && C > 0 && G > 0, "groupnorm: bad args");
+  if (workspace && groupnorm_big_eligible(B, HW, C, G, in_f16))
+    return groupnorm_big(x, y, gamma, beta, B, HW, C, G, eps, silu, out_f16, workspace, ws_bytes, (cudaStream_t)stream);
+  return groupnorm(x, y, gamma, beta, B, HW, C, G, eps, silu, in_f16, out_f16, (cudaStream_t)stream);
 }
 
 extern "C" int cnb_groupnorm(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C,

@@ -1,0 +1,226 @@
+// GroupNorm (+SiLU) for samples whose [HW, C] fp16 slab does not fit one CTA's shared memory (VAE decoder: 128x128x256 =
+// 8 MB per sample; CelebHQ-latent students: 32x32x256 = 512 KB).  The one-CTA-per-sample kernels of groupnorm.cu then
+// sweep the slab three times from L2 / HBM with B CTAs on 148 SMs; here a sample is split over S row ranges:
+//
+//   stats kernel   grid (S, B): each CTA streams its rows ONCE with 16-byte loads (thread <-> 8 fixed channels) and
+//                  accumulates shifted sums  sum(x - p), sum((x - p)^2)  per channel, p = the channel's value in the
+//                  CTA's first row (no cancellation: |mean - p| ~ sigma); per-channel (n, mean, M2) are merged per
+//                  group with Chan's parallel-variance formula and written as one float4 per (sample, range, group)
+//   apply kernel   grid (S, B): merges the S partials of its sample (Chan again, double accumulators), folds gamma /
+//                  beta into one FMA per element, applies SiLU (tanh form for fp16 outputs) and stores 16 bytes
+//
+// Algorithmic bytes: 2 B read + 2 B written per element; the second read of a range follows its first within a few
+// hundred microseconds and is an L2 hit whenever B * slab stays under the 126 MB L2, else DRAM sees 2 reads + 1 write.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace cnb {
+
+namespace gnb {
+
+constexpr int NT = 256;
+
+__device__ __forceinline__ void widen8(const uint4& raw, float* v) {
+  const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ float silu_tanh(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
+// (n_a, mean_a, M2_a) <- merge with (n_b, mean_b, M2_b)
+template <typename T>
+__device__ __forceinline__ void chan_merge(T& n, T& mean, T& m2, T nb, T mb, T m2b) {
+  if (nb == T(0)) return;
+  const T nt = n + nb, d = mb - mean;
+  mean += d * (nb / nt);
+  m2 += m2b + d * d * (n * nb / nt);
+  n = nt;
+}
+
+__global__ void __launch_bounds__(NT)
+stats_kernel(const __half* __restrict__ x, float4* __restrict__ partial, int HW, int C, int G, int rows_per_cta) {
+  extern __shared__ float sm[];
+  const int C8 = C >> 3;
+  const int R = NT / C8;                       // pixel rows per sweep
+  float* part = sm;                            // [R][C][2]  shifted sum, shifted sum of squares
+  float* cstat = part + (size_t)R * C * 2;     // [C][2]     per-channel mean, M2
+  const int tid = threadIdx.x, col = tid % C8, r0 = tid / C8;
+  const int S = gridDim.x, s = blockIdx.x, b = blockIdx.y;
+  const int row0 = s * rows_per_cta;
+  const int nrows = max(0, min(rows_per_cta, HW - row0));
+  const uint4* xs = reinterpret_cast<const uint4*>(x) + ((size_t)b * HW + row0) * C8;
+  float piv[8], sum[8], sq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { piv[i] = 0.f; sum[i] = 0.f; sq[i] = 0.f; }
+  if (r0 < R && nrows > 0) {
+    widen8(__ldg(xs + col), piv);
+    int row = r0;
+    // two rows in flight per iteration
+    for (; row + R < nrows; row += 2 * R) {
+      const uint4 a = __ldcs(xs + (size_t)row * C8 + col), c = __ldcs(xs + (size_t)(row + R) * C8 + col);
+      float va[8], vc[8];
+      widen8(a, va);
+      widen8(c, vc);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float da = va[i] - piv[i], dc = vc[i] - piv[i];
+        sum[i] += da + dc;
+        sq[i] = fmaf(da, da, fmaf(dc, dc, sq[i]));
+      }
+    }
+    if (row < nrows) {
+      float va[8];
+      widen8(__ldcs(xs + (size_t)row * C8 + col), va);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float da = va[i] - piv[i];
+        sum[i] += da;
+        sq[i] = fmaf(da, da, sq[i]);
+      }
+    }
+  }
+  if (r0 < R) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      part[((size_t)r0 * C + col * 8 + i) * 2] = sum[i];
+      part[((size_t)r0 * C + col * 8 + i) * 2 + 1] = sq[i];
+    }
+  }
+  __syncthreads();
+  // per channel: shifted sums over the R row classes -> (mean, M2) over the CTA's nrows rows
+  for (int c = tid; c < C; c += NT) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int r = 0; r < R; ++r) {
+      s1 += part[((size_t)r * C + c) * 2];
+      s2 += part[((size_t)r * C + c) * 2 + 1];
+    }
+    const float p = nrows > 0 ? __half2float(x[((size_t)b * HW + row0) * C + c]) : 0.f;
+    const float n = (float)nrows;
+    const float dm = nrows > 0 ? s1 / n : 0.f;
+    cstat[2 * c] = p + dm;
+    cstat[2 * c + 1] = fmaxf(s2 - s1 * dm, 0.f);
+  }
+  __syncthreads();
+  const int cg = C / G;
+  for (int g = tid; g < G; g += NT) {
+    float n = 0.f, mean = 0.f, m2 = 0.f;
+    for (int c = 0; c < cg; ++c) chan_merge(n, mean, m2, (float)nrows, cstat[2 * (g * cg + c)], cstat[2 * (g * cg + c) + 1]);
+    partial[((size_t)b * S + s) * G + g] = make_float4(n, mean, m2, 0.f);
+  }
+}
+
+template <bool SILU, bool HALF>
+__global__ void __launch_bounds__(NT)
+apply_kernel(const __half* __restrict__ x, void* __restrict__ y, const float4* __restrict__ partial,
+             const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C, int G, float eps,
+             int rows_per_cta, int S_stats) {
+  extern __shared__ float sm[];
+  float* g_mean = sm;            // [G]
+  float* g_rstd = sm + G;        // [G]
+  const int C8 = C >> 3;
+  const int R = NT / C8;
+  const int tid = threadIdx.x, col = tid % C8, r0 = tid / C8;
+  const int s = blockIdx.x, b = blockIdx.y;
+  for (int g = tid; g < G; g += NT) {
+    double n = 0.0, mean = 0.0, m2 = 0.0;
+    for (int q = 0; q < S_stats; ++q) {
+      const float4 p = __ldg(partial + ((size_t)b * S_stats + q) * G + g);
+      chan_merge(n, mean, m2, (double)p.x, (double)p.y, (double)p.z);
+    }
+    g_mean[g] = (float)mean;
+    g_rstd[g] = rsqrtf((float)(m2 / n) + eps);
+  }
+  __syncthreads();
+  if (r0 >= R) return;
+  const int cg = C / G;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = col * 8 + i, g = c / cg;
+    sc[i] = __ldg(gamma + c) * g_rstd[g];
+    sh[i] = fmaf(-g_mean[g], sc[i], __ldg(beta + c));
+  }
+  const int row0 = s * rows_per_cta;
+  const int nrows = max(0, min(rows_per_cta, HW - row0));
+  const uint4* xs = reinterpret_cast<const uint4*>(x) + ((size_t)b * HW + row0) * C8;
+  for (int row = r0; row < nrows; row += R) {
+    float v[8];
+    widen8(__ldcs(xs + (size_t)row * C8 + col), v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[i] = fmaf(v[i], sc[i], sh[i]);
+      if (SILU) v[i] = HALF ? silu_tanh(v[i]) : silu_f(v[i]);
+    }
+    const size_t o = ((size_t)b * HW + row0 + row) * C8 + col;
+    if (HALF) {
+      uint4 out;
+      __half2* h = reinterpret_cast<__half2*>(&out);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+      reinterpret_cast<uint4*>(y)[o] = out;
+    } else {
+      float4* yo = reinterpret_cast<float4*>(y) + 2 * o;
+      yo[0] = make_float4(v[0], v[1], v[2], v[3]);
+      yo[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+}
+
+// row ranges per sample: enough CTAs to fill the GPU ~8 deep, at least 4 sweeps of rows per CTA
+static int pick_split(int B, int HW, int C) {
+  const int R = NT / (C / 8);
+  int S = ceil_div(148 * 8, B);
+  const int maxS = HW / (4 * R) > 0 ? HW / (4 * R) : 1;
+  if (S > maxS) S = maxS;
+  if (S < 1) S = 1;
+  return S;
+}
+
+}  // namespace gnb
+
+bool groupnorm_big_eligible(int B, int HW, int C, int G, int in_f16) {
+  if (!in_f16 || C % 8 || C % G || C / 8 > gnb::NT || B > 65535) return false;
+  return (size_t)HW * C * 2 > 110 * 1024;                 // beyond the staged one-CTA-per-sample kernel
+}
+
+size_t groupnorm_big_workspace(int B, int HW, int C, int G) {
+  return (size_t)B * gnb::pick_split(B, HW, C) * G * sizeof(float4);
+}
+
+int groupnorm_big(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G, float eps,
+                  int silu, int out_f16, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  using namespace gnb;
+  const int S = pick_split(B, HW, C);
+  CNB_REQUIRE(workspace && ws_bytes >= (size_t)B * S * G * sizeof(float4), "groupnorm: workspace too small");
+  const int rows = ceil_div(HW, S);
+  const int R = NT / (C / 8);
+  const size_t smem_stats = ((size_t)R * C * 2 + 2 * C) * sizeof(float);
+  CNB_REQUIRE(smem_stats <= 48 * 1024, "groupnorm_big: smem %zu too large", smem_stats);
+  float4* partial = reinterpret_cast<float4*>(workspace);
+  stats_kernel<<<dim3(S, B), NT, smem_stats, st>>>(reinterpret_cast<const __half*>(x), partial, HW, C, G, rows);
+  CNB_LAUNCH_CHECK();
+  const size_t smem_apply = 2 * G * sizeof(float);
+  const __half* xh = reinterpret_cast<const __half*>(x);
+  const dim3 grid(S, B);
+  if (silu) {
+    if (out_f16) apply_kernel<true, true><<<grid, NT, smem_apply, st>>>(xh, y, partial, gamma, beta, HW, C, G, eps, rows, S);
+    else apply_kernel<true, false><<<grid, NT, smem_apply, st>>>(xh, y, partial, gamma, beta, HW, C, G, eps, rows, S);
+  } else {
+    if (out_f16) apply_kernel<false, true><<<grid, NT, smem_apply, st>>>(xh, y, partial, gamma, beta, HW, C, G, eps, rows, S);
+    else apply_kernel<false, false><<<grid, NT, smem_apply, st>>>(xh, y, partial, gamma, beta, HW, C, G, eps, rows, S);
+  }
+  CNB_LAUNCH_CHECK();
+  return CNB_OK;
+}
+
+}  // namespace cnb

@@ -313,7 +313,8 @@ def run_up(block, x, skip, temb, mode, cat=None):
     x = cat
     for j in range(block.num_layers):
         x = block._resnet(j, x, temb, mode)
-        x = block._attention(j, x, mode)
+        if block.attn:                                     # always on in the U-Nets, per-level in the VAE decoder
+            x = block._attention(j, x, mode)
     return x
 
 

@@ -1,8 +1,8 @@
 """Drop-in for the reference's models/blocks.py: the configurable (norm groups, heads, per-block attention flag)
 Down / Mid / Up blocks used by the LDM U-Net.  Reference: DownBlock blocks.py:31-150, MidBlock :153-271,
 UpBlockUnet :377-503.  Cross-attention branches (:91-104,:136-146,:251-261,:488-501) are dead for every shipped
-config and are not built (constructing with cross_attn=True raises NotImplementedError); the VAE-only `UpBlock`
-(:274-374) belongs to VAE.decode, the next row after the hot path.
+config and are not built (constructing with cross_attn=True raises NotImplementedError).  `UpBlock` (:274-374) is the
+VAE decoder's block (no skip, ConvTranspose over in_channels, optional attention) used by models/vae.py.
 """
 import torch.nn as nn
 
@@ -65,6 +65,22 @@ class UpBlockUnet(_Block):
         self.up_sample_conv = nn.ConvTranspose2d(half, half, 4, 2, 1) if up_sample else nn.Identity()
 
     def forward(self, x, out_down=None, t_emb=None, context=None):
+        mode = rt.get_mode()
+        skip = None if out_down is None else ops.nchw_to_nhwc(E._check_x(out_down))
+        return self._io(lambda h: E.run_up(self, h, skip, self._temb(t_emb), mode), x)
+
+
+class UpBlock(_Block):
+    """blocks.py:284-374: ConvTranspose2d(in, in, 4, 2, 1) or identity, then num_layers x [resnet, (self-attn)]."""
+
+    def __init__(self, in_channels, out_channels, t_emb_dim, up_sample, num_heads, num_layers, attn, norm_channels):
+        super().__init__()
+        self.num_layers, self.up_sample, self.attn = num_layers, up_sample, attn
+        self._build(in_channels, out_channels, t_emb_dim, num_layers, num_layers if attn else 0, norm_channels,
+                    num_heads)
+        self.up_sample_conv = nn.ConvTranspose2d(in_channels, in_channels, 4, 2, 1) if up_sample else nn.Identity()
+
+    def forward(self, x, out_down=None, t_emb=None):
         mode = rt.get_mode()
         skip = None if out_down is None else ops.nchw_to_nhwc(E._check_x(out_down))
         return self._io(lambda h: E.run_up(self, h, skip, self._temb(t_emb), mode), x)

@@ -55,6 +55,8 @@ class MidBlock(_Block):
 
 
 class UpBlock(_Block):
+    attn = True
+
     def __init__(self, in_channels, out_channels, t_emb_dim, up_sample=True, num_heads=4, num_layers=1):
         super().__init__()
         self.num_layers, self.up_sample = num_layers, up_sample

@@ -99,13 +99,22 @@ def conv(x, weight, kind, cout, *, bias=None, temb=None, temb_ld=0, temb_per_sam
 
 
 def groupnorm(x, gamma, beta, groups, silu, eps=1e-5, out_f16=False):
-    """out_f16: emit the normalised activations as fp16, the operand type of the kind::f16 convolution after it."""
+    """out_f16: emit the normalised activations as fp16, the operand type of the kind::f16 convolution after it.
+    Samples too large for one CTA (VAE decoder levels) take the split-statistics kernel pair, whose scratch buffer is
+    allocated here (torch's caching allocator, so it is legal under CUDA-graph capture)."""
     rt.require_cuda(x, gamma, beta)
     B, H, W, C = x.shape
     y = torch.empty((B, H, W, C), device=x.device, dtype=torch.float16 if out_f16 else torch.float32)
+    in16 = 1 if x.dtype == torch.float16 else 0
+    ws_bytes = rt.lib().cnb_groupnorm_workspace_bytes(B, H * W, C, groups, in16)
+    if ws_bytes:
+        ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+        rt.check(rt.lib().cnb_groupnorm_ws(x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, H * W, C,
+                                           groups, eps, 1 if silu else 0, in16, 1 if out_f16 else 0, ws.data_ptr(),
+                                           ws_bytes, rt.stream()))
+        return y
     rt.check(rt.lib().cnb_groupnorm(x.data_ptr(), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), B, H * W, C,
-                                    groups, eps, 1 if silu else 0, 1 if x.dtype == torch.float16 else 0,
-                                    1 if out_f16 else 0, rt.stream()))
+                                    groups, eps, 1 if silu else 0, in16, 1 if out_f16 else 0, rt.stream()))
     return y
 
 

@@ -49,6 +49,9 @@ _SIGS = {
     "cnb_cast_f16": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
     "cnb_groupnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int,
                               c_int, c_int, c_void_p]),
+    "cnb_groupnorm_workspace_bytes": (ctypes.c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "cnb_groupnorm_ws": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int,
+                                 c_int, c_int, c_void_p, ctypes.c_size_t, c_void_p]),
     "cnb_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "cnb_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "cnb_attention_tc05": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -86,5 +86,15 @@ TINY_LDM_PARAMS = dict(hint_channels=3, down_channels=[32, 64, 64, 128], mid_cha
                        norm_channels=8, num_heads=4, conv_out_channels=32, num_down_layers=1,
                        num_mid_layers=1, num_up_layers=1)
 
+# config/celebhq.yaml:27-38 (im_channels 3, im_size 128 -> latent 4 x 32 x 32)
+CELEBHQ_VAE_PARAMS = dict(z_channels=4, codebook_size=8192, down_channels=[128, 256, 384], mid_channels=[384],
+                          down_sample=[True, True], attn_down=[False, False], norm_channels=32, num_heads=4,
+                          num_down_layers=2, num_mid_layers=2, num_up_layers=2)
+
+# small VAE that exercises what the CelebHQ one skips: a decoder / encoder MidBlock and an attention UpBlock
+TINY_VAE_PARAMS = dict(z_channels=4, codebook_size=16, down_channels=[16, 32, 64], mid_channels=[64, 64],
+                       down_sample=[True, True], attn_down=[False, True], norm_channels=8, num_heads=4,
+                       num_down_layers=1, num_mid_layers=1, num_up_layers=1)
+
 MNIST_DIFFUSION = dict(num_timesteps=1000, beta_start=0.0001, beta_end=0.02)
 CELEBHQ_DIFFUSION = dict(num_timesteps=1000, beta_start=0.0015, beta_end=0.0195)

@@ -18,6 +18,7 @@
 #ifndef CNB200_H
 #define CNB200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -114,6 +115,13 @@ int cnb_cast_f16(const float* src, void* dst, long long n, cnb_stream_t stream);
  */
 int cnb_groupnorm(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
                   float eps, int silu, int in_f16, int out_f16, cnb_stream_t stream);
+/* Large samples (fp16 slab of HW * C * 2 bytes beyond one CTA's shared memory: the VAE decoder's 64x64 / 128x128
+ * levels, vae.py:102-114 through blocks.py:347-374) are normalised by a split-statistics + apply kernel pair that
+ * needs a scratch buffer: cnb_groupnorm_workspace_bytes returns its size (0: cnb_groupnorm's one-CTA-per-sample
+ * kernels are the right ones), cnb_groupnorm_ws takes it (workspace == NULL behaves like cnb_groupnorm). */
+size_t cnb_groupnorm_workspace_bytes(int B, int HW, int C, int G, int in_f16);
+int cnb_groupnorm_ws(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
+                     float eps, int silu, int in_f16, int out_f16, void* workspace, size_t ws_bytes, cnb_stream_t stream);
 
 /*
  * Self-attention core on packed projections: qkv is [B, L, 3E] (q | k | v, heads split along E), out is [B, L, E].

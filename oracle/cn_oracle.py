@@ -143,6 +143,56 @@ def up_block(sd, p, x, skip, temb, n_layers, groups, heads, up_sample):
     return x
 
 
+def vae_up_block(sd, p, x, n_layers, groups, heads, attn, up_sample):
+    """models/blocks.py:347-374 (VAE UpBlock: ConvTranspose over in_channels, no skip, optional self-attention)."""
+    if up_sample:
+        x = F.conv_transpose2d(x, sd[p + "up_sample_conv.weight"], sd[p + "up_sample_conv.bias"],
+                               stride=2, padding=1)
+    for j in range(n_layers):
+        x = resnet(sd, p, j, x, None, groups)
+        if attn:
+            x = self_attention(sd, p, j, x, groups, heads)
+    return x
+
+
+# --------------------------------------------------------------------------------------------
+# VAE (models/vae.py) - the step after the sampling loop in tools/sample_ldm_controlnet.py:54-56
+# --------------------------------------------------------------------------------------------
+def vae_decode(sd, cfg, z):
+    """models/vae.py:102-114: post_quant_conv -> decoder_conv_in -> MidBlocks (reversed) -> UpBlocks (reversed)
+    -> GroupNorm -> SiLU -> decoder_conv_out."""
+    dc, mc, g, heads = cfg["down_channels"], cfg["mid_channels"], cfg["norm_channels"], cfg["num_heads"]
+    up_sample = list(reversed(cfg["down_sample"]))          # vae.py:33 builds it but the blocks index down_sample[i-1]
+    del up_sample
+    h = _conv(sd, "post_quant_conv", z)
+    h = _conv(sd, "decoder_conv_in", h, padding=1)
+    for k, _ in enumerate(reversed(range(1, len(mc)))):
+        h = mid_block(sd, f"decoder_mids.{k}.", h, None, cfg["num_mid_layers"], g, heads)
+    for k, i in enumerate(reversed(range(1, len(dc)))):
+        h = vae_up_block(sd, f"decoder_layers.{k}.", h, cfg["num_up_layers"], g, heads, cfg["attn_down"][i - 1],
+                         cfg["down_sample"][i - 1])
+    h = F.silu(_gn(sd, "decoder_norm_out", h, g))
+    return _conv(sd, "decoder_conv_out", h, padding=1)
+
+
+def vae_encode(sd, cfg, x, noise=None):
+    """models/vae.py:86-100.  Returns (sample, encoder_output); `noise` replaces the reference's
+    torch.randn(mean.shape) (CPU default generator), sample is None when it is not given."""
+    dc, mc, g, heads = cfg["down_channels"], cfg["mid_channels"], cfg["norm_channels"], cfg["num_heads"]
+    h = _conv(sd, "encoder_conv_in", x, padding=1)
+    for i in range(len(dc) - 1):
+        h = down_block(sd, f"encoder_layers.{i}.", h, None, cfg["num_down_layers"], g, heads, cfg["attn_down"][i],
+                       cfg["down_sample"][i])
+    for i in range(len(mc) - 1):
+        h = mid_block(sd, f"encoder_mids.{i}.", h, None, cfg["num_mid_layers"], g, heads)
+    h = F.silu(_gn(sd, "encoder_norm_out", h, g))
+    out = _conv(sd, "pre_quant_conv", _conv(sd, "encoder_conv_out", h, padding=1))
+    if noise is None:
+        return None, out
+    mean, logvar = torch.chunk(out, 2, dim=1)
+    return mean + torch.exp(0.5 * logvar) * noise, out
+
+
 # --------------------------------------------------------------------------------------------
 # U-Net pieces
 # --------------------------------------------------------------------------------------------

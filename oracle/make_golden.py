@@ -72,9 +72,43 @@ def trajectory(model, sched, x, hint, steps, name):
 
 
 @torch.no_grad()
+def make_vae():
+    """models/vae.py decode / encode on the tiny VAE (decoder MidBlock + attention UpBlock) and, at batch 1, on the
+    CelebHQ autoencoder_params (config/celebhq.yaml:27-38): output statistics + a strided sample of the image."""
+    from models.vae import VAE as RefVAE
+    cfg = syn.TINY_VAE_PARAMS
+    m = fill(RefVAE(3, cfg))
+    z = syn.det_noise("vae_tiny:z", (2, 4, 8, 8))
+    x = syn.det_noise("vae_tiny:x", (2, 3, 32, 32))
+    rec = {"dec": m.decode(z).numpy()}
+    noise = syn.det_noise("vae_tiny:n", (2, 4, 8, 8))
+    import models.vae as ref_vae_mod
+    orig = ref_vae_mod.torch.randn
+    ref_vae_mod.torch.randn = lambda *a, **k: noise
+    try:
+        sample, enc = m.encode(x)
+    finally:
+        ref_vae_mod.torch.randn = orig
+    rec["enc_out"], rec["enc_sample"] = enc.numpy(), sample.numpy()
+    np.savez_compressed(os.path.join(OUT, "vae_tiny.npz"), **rec)
+    m = fill(RefVAE(3, syn.CELEBHQ_VAE_PARAMS))
+    z = syn.det_noise("vae_celebhq:z", (1, 4, 32, 32))
+    img = m.decode(z)
+    np.savez_compressed(os.path.join(OUT, "vae_celebhq.npz"), dec_strided=img[:, :, ::4, ::4].numpy(),
+                        dec_sum=img.double().sum().numpy(), dec_sqsum=(img.double() ** 2).sum().numpy())
+    import json
+    with open(os.path.join(OUT, "state_dict_manifest_vae.json"), "w") as f:
+        json.dump({"vae_tiny": {k: list(v.shape) for k, v in RefVAE(3, cfg).state_dict().items()},
+                   "vae_celebhq": {k: list(v.shape) for k, v in m.state_dict().items()}}, f)
+    print("vae", img.shape)
+
+
+@torch.no_grad()
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
+    if "--only-vae" in sys.argv:
+        return make_vae()
 
     # ---- DDPM ControlNet: tiny / mnist / cifar
     for name, cfg, B, ts in (("tiny", syn.TINY_PARAMS, 2, (999, 37, 0)),
@@ -164,6 +198,7 @@ def main():
         man[tag] = {k: list(v.shape) for k, v in mod.state_dict().items()}
     with open(os.path.join(OUT, "state_dict_manifest.json"), "w") as f:
         json.dump(man, f)
+    make_vae()
     print("done ->", OUT)
 
 

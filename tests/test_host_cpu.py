@@ -58,6 +58,13 @@ def test_state_dict_layout_matches_reference_manifest():
     assert not hasattr(built["unet_mnist_noup"], "ups") and not hasattr(built["unet_mnist_noup"], "conv_out")
     n = sum(p.numel() for p in built["controlnet_mnist"].parameters())
     assert n == 20070545
+    with open(os.path.join(GOLDEN, "state_dict_manifest_vae.json")) as f:
+        man = json.load(f)
+    vae = _mod("models.vae")
+    for tag, mod in (("vae_tiny", vae.VAE(3, syn.TINY_VAE_PARAMS)), ("vae_celebhq", vae.VAE(3, syn.CELEBHQ_VAE_PARAMS))):
+        mine = {k: list(v.shape) for k, v in mod.state_dict().items()}
+        assert list(mine.keys()) == list(man[tag].keys()), tag
+        assert mine == man[tag], tag
 
 
 def test_default_init_is_seed_identical_to_reference_when_present():

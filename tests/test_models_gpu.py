@@ -186,3 +186,27 @@ def test_hint_cache_and_weight_cache_invalidate(rt):
         sd = {k: v.cpu() for k, v in m.state_dict().items()}
         want = O.controlnet_ddpm_forward(sd, cfg, x, torch.tensor([37]), hint)
         assert rel_l2(e3.cpu(), want) < 1e-4
+
+
+def test_vae_vs_reference_golden(rt):
+    """models/vae.py decode / encode against the reference's outputs: tiny VAE (decoder MidBlock +
+    attention UpBlock) and the full-size CelebHQ autoencoder at batch 1."""
+    VAE = _mod("models.vae").VAE
+    m = _fill(VAE(3, syn.TINY_VAE_PARAMS))
+    g = golden("vae_tiny")
+    z = syn.det_noise("vae_tiny:z", (2, 4, 8, 8)).cuda()
+    x = syn.det_noise("vae_tiny:x", (2, 3, 32, 32)).cuda()
+    big = _fill(VAE(3, syn.CELEBHQ_VAE_PARAMS))
+    gb = golden("vae_celebhq")
+    zb = syn.det_noise("vae_celebhq:z", (1, 4, 32, 32)).cuda()
+    for mode in _modes(rt):
+        rt.set_mode(mode)
+        with torch.no_grad():
+            assert rel_l2(m.decode(z).cpu(), g["dec"]) < TOL[mode], mode
+            assert rel_l2(m._encode_out(x, rt.get_mode()).cpu(), g["enc_out"]) < TOL[mode], mode
+            sample, out = m.encode(x)
+            assert tuple(sample.shape) == (2, 4, 8, 8) and tuple(out.shape) == (2, 8, 8, 8)
+            img = big.decode(zb)
+        assert tuple(img.shape) == (1, 3, 128, 128)
+        assert rel_l2(img[:, :, ::4, ::4].cpu(), gb["dec_strided"]) < TOL[mode], mode
+    assert rt.lib().cnb_tc_error_flag() == 0

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import golden, inputs, rel_l2, syn, ROOT
+from helpers import det_sd_for, golden, inputs, rel_l2, syn, ROOT
 
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import cn_oracle as O  # noqa: E402
@@ -129,3 +129,29 @@ def test_oracle_vs_live_reference_default_init():
         sys.path.remove("/root/reference")
         for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
             del sys.modules[k]
+
+
+def test_vae_vs_golden():
+    """models/vae.py decode / encode (the step after the LDM sampling loop) against the reference's outputs."""
+    cfg = syn.TINY_VAE_PARAMS
+    sd = det_sd_for(lambda: importlib.import_module("controlnet-pytorch_b200.models.vae").VAE(3, cfg), "vae_tiny")
+    g = golden("vae_tiny")
+    with torch.no_grad():
+        dec = O.vae_decode(sd, cfg, syn.det_noise("vae_tiny:z", (2, 4, 8, 8)))
+        sample, enc = O.vae_encode(sd, cfg, syn.det_noise("vae_tiny:x", (2, 3, 32, 32)),
+                                   noise=syn.det_noise("vae_tiny:n", (2, 4, 8, 8)))
+    assert rel_l2(dec, g["dec"]) < 2e-6
+    assert rel_l2(enc, g["enc_out"]) < 2e-6
+    assert rel_l2(sample, g["enc_sample"]) < 2e-6
+
+
+def test_vae_celebhq_decode_vs_golden():
+    """Full-size CelebHQ autoencoder (config/celebhq.yaml:27-38) decode at batch 1: strided image sample + moments."""
+    cfg = syn.CELEBHQ_VAE_PARAMS
+    sd = det_sd_for(lambda: importlib.import_module("controlnet-pytorch_b200.models.vae").VAE(3, cfg), "vae_celebhq")
+    g = golden("vae_celebhq")
+    with torch.no_grad():
+        img = O.vae_decode(sd, cfg, syn.det_noise("vae_celebhq:z", (1, 4, 32, 32)))
+    assert tuple(img.shape) == (1, 3, 128, 128)
+    assert rel_l2(img[:, :, ::4, ::4], g["dec_strided"]) < 5e-6
+    assert abs(float(img.double().pow(2).sum()) / float(g["dec_sqsum"]) - 1) < 1e-5
