@@ -209,6 +209,21 @@ __global__ void scale_rows_kernel(const float* __restrict__ a, const float* __re
   out[i] = v;
 }
 
+// x0 = clamp((x_t - s1[t_b] * eps) / s2[t_b], -1, 1) with per-sample timesteps: the teacher-side conversion of a noise
+// prediction (distribution_matching_controlnet.py:204-214, consistency_controlnet_distilled.py:219-227).  Same operation
+// order as the reference (mul, sub, div, clamp), no FMA contraction: bit-identical to the fp32 ATen expression.
+__global__ void x0_from_eps_kernel(const float* __restrict__ xt, const float* __restrict__ eps,
+                                   const float* __restrict__ sqrt_one_minus, const float* __restrict__ sqrt_alpha,
+                                   const long long* __restrict__ t, int t_count, float* __restrict__ out,
+                                   long long per_sample, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = (int)(i / per_sample);
+  const long long tb = t[t_count == 1 ? 0 : b];
+  const float v = __fdiv_rn(__fsub_rn(xt[i], __fmul_rn(sqrt_one_minus[tb], eps[i])), sqrt_alpha[tb]);
+  out[i] = fminf(fmaxf(v, -1.0f), 1.0f);
+}
+
 // ------------------------------------------------------------------------------------------------
 // layout plumbing
 // ------------------------------------------------------------------------------------------------
@@ -381,6 +396,18 @@ extern "C" int cnb_scale_rows(const float* a, const float* x, const float* c, co
   long long total = (long long)B * per_sample;
   CNB_REQUIRE(total > 0 && (y == nullptr || c != nullptr), "scale_rows: bad args");
   scale_rows_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)s>>>(a, x, c, y, out, per_sample, total);
+  CNB_LAUNCH_CHECK();
+  return CNB_OK;
+}
+
+extern "C" int cnb_x0_from_eps(const float* xt, const float* eps, const float* sqrt_one_minus, const float* sqrt_alpha,
+                               const int64_t* t, int t_count, int num_timesteps, float* out, int B, long long per_sample,
+                               cnb_stream_t s) {
+  long long total = (long long)B * per_sample;
+  CNB_REQUIRE(xt && eps && sqrt_one_minus && sqrt_alpha && t && out && total > 0 && (t_count == 1 || t_count == B) &&
+                  num_timesteps > 0, "x0_from_eps: bad args");
+  x0_from_eps_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)s>>>(
+      xt, eps, sqrt_one_minus, sqrt_alpha, reinterpret_cast<const long long*>(t), t_count, out, per_sample, total);
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }

@@ -113,6 +113,31 @@ class ConsistencyControlNetDistilled(nn.Module):
     def forward(self, x_t, sigma, hint):
         return self.student(x_t, sigma, hint)
 
+    def sigma_to_timestep(self, sigma):
+        """Closest entry of the teacher's sigma schedule sqrt((1 - abar) / abar) (:230-257): a 1000-entry host-side
+        table lookup (torch ops on the model's device, not per-sample work)."""
+        if not isinstance(sigma, torch.Tensor):
+            sigma = torch.tensor(sigma, dtype=torch.float32)
+        device = next(self.parameters()).device
+        sigma = sigma.to(device)
+        if hasattr(self, 'teacher_scheduler'):
+            acp = self.teacher_scheduler.alpha_cum_prod.to(device)
+        else:
+            betas = torch.linspace(0.0001, 0.02, self.num_timesteps, device=device)
+            acp = torch.cumprod(1.0 - betas, dim=0)
+        schedule = torch.sqrt((1 - acp) / acp)
+        if sigma.dim() == 0:
+            sigma = sigma.unsqueeze(0)
+        t = torch.argmin(torch.abs(schedule.unsqueeze(0) - sigma.unsqueeze(-1)), dim=-1)
+        return t.long().clamp(0, self.num_timesteps - 1)
+
+    def get_ddpm_teacher_prediction(self, x_t, sigma, hint):
+        """DDPM teacher's x_0 prediction at the timestep closest to sigma (:201-228)."""
+        if self.ddpm_teacher is None:
+            raise ValueError("DDPM teacher not initialized")
+        from ._student_common import teacher_x0
+        return teacher_x0(self.ddpm_teacher, self.teacher_scheduler, x_t, self.sigma_to_timestep(sigma.squeeze()), hint)
+
     def generate(self, hint, shape, num_steps=1, guidance_scale=1.0):
         """Single-step (:381-389) and multi-step (:390-409) sampling.  x_T / re-noising draws use torch's CUDA
         generator exactly like the reference (`torch.randn(shape, device=device)`), so seeded runs see the same

@@ -78,3 +78,8 @@ class DistributionMatchingControlNetDistilled(nn.Module):
 
     def forward(self, x_t, t, hint):
         return self.student(x_t, t, hint)
+
+    def get_teacher_prediction(self, x_t, t, hint):
+        """Teacher's noise prediction converted to x_0 (:191-216), forward-only on the libcnb200 kernels."""
+        from ._student_common import teacher_x0
+        return teacher_x0(self.teacher, self.teacher_scheduler, x_t, t, hint)

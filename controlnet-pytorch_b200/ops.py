@@ -241,6 +241,19 @@ def philox_normal(shape, device, seed, step, elem_offset=0):
     return out
 
 
+def x0_from_eps(xt, eps, sqrt_one_minus, sqrt_alpha, t):
+    """clamp((xt - sqrt_one_minus[t] * eps) / sqrt_alpha[t], -1, 1); t: int64 (1,) or (B,) on the device."""
+    rt.require_cuda(xt, eps, sqrt_one_minus, sqrt_alpha, t)
+    if t.dtype != torch.int64 or t.numel() not in (1, xt.shape[0]):
+        raise rt.CnbError("x0_from_eps: t must be int64 with 1 or B entries")
+    out = torch.empty_like(xt)
+    B = xt.shape[0]
+    rt.check(rt.lib().cnb_x0_from_eps(xt.data_ptr(), eps.data_ptr(), sqrt_one_minus.data_ptr(), sqrt_alpha.data_ptr(),
+                                      t.data_ptr(), t.numel(), sqrt_alpha.numel(), out.data_ptr(), B,
+                                      xt.numel() // B, rt.stream()))
+    return out
+
+
 def scale_rows(a, x, c=None, y=None):
     rt.require_cuda(a, x, c, y)
     out = torch.empty_like(x)

@@ -108,6 +108,36 @@ class DDPMSampler:
             self._pos += 1
 
 
+class LDMSampler(DDPMSampler):
+    """tools/sample_ldm_controlnet.py:21-64: the same timestep loop on VAE latents, then `vae.decode` of the final
+    latents only (:51-53), clamp to [-1, 1] and map to [0, 1] (:57-58).  Decoding runs in chunks so that the
+    128x128x256-channel decoder activations of a large batch stay bounded (2.1 GB per 256 samples and tensor)."""
+
+    def __init__(self, model, scheduler, vae, seed=0, use_graph=True, decode_chunk=256):
+        super().__init__(model, scheduler, seed=seed, use_graph=use_graph)
+        self.vae, self.decode_chunk = vae, int(decode_chunk)
+
+    @torch.no_grad()
+    def decode(self, latents, to_unit_range=True):
+        rt.require_cuda(latents)
+        outs = []
+        for lo in range(0, latents.shape[0], self.decode_chunk):
+            ims = self.vae.decode(latents[lo:lo + self.decode_chunk].contiguous())
+            if to_unit_range:
+                ims = (torch.clamp(ims, -1., 1.) + 1) / 2
+            outs.append(ims)
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+    @torch.no_grad()
+    def sample_images(self, x_T, hint, steps=None, elem_offset=0, zs=None, to_unit_range=True):
+        """Returns (images, final latents).  zs: injected per-step noise (eager loop, parity tests)."""
+        if zs is not None:
+            xt, _ = self.sample_eager(x_T, hint, steps, zs, elem_offset)
+        else:
+            xt, _ = self.sample(x_T, hint, steps=steps, elem_offset=elem_offset)
+        return self.decode(xt, to_unit_range), xt
+
+
 def shard_bounds(total, world, rank):
     """Contiguous slice [lo, hi) of the batch owned by `rank` (remainder spread over the first ranks)."""
     base, rem = divmod(total, world)
@@ -117,9 +147,10 @@ def shard_bounds(total, world, rank):
 
 @torch.no_grad()
 def sample_data_parallel(model, scheduler, shape, hint_fn, steps=None, seed=0, group=None, use_graph=True,
-                         gather=True):
+                         gather=True, vae=None):
     """One job over all ranks of `group`: rank r draws and denoises samples [lo, hi) and the final samples are
-    all-gathered once.  `hint_fn(lo, hi)` returns this shard's hint tensor on the local device."""
+    all-gathered once.  `hint_fn(lo, hi)` returns this shard's hint tensor on the local device.  With `vae` the
+    shard's final latents are decoded locally (LDM path) and the images are what is gathered."""
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -129,9 +160,12 @@ def sample_data_parallel(model, scheduler, shape, hint_fn, steps=None, seed=0, g
     for d in shape[1:]:
         per *= d
     dev = torch.device("cuda", torch.cuda.current_device())
-    smp = DDPMSampler(model, scheduler, seed=seed, use_graph=use_graph)
+    smp = (DDPMSampler(model, scheduler, seed=seed, use_graph=use_graph) if vae is None else
+           LDMSampler(model, scheduler, vae, seed=seed, use_graph=use_graph))
     x_T = smp.draw_xT((hi - lo,) + tuple(shape[1:]), dev, elem_offset=lo * per)
     xt, x0 = smp.sample(x_T, hint_fn(lo, hi), steps=steps, elem_offset=lo * per)
+    if vae is not None:
+        xt = smp.decode(xt)
     if not gather or world == 1:
         return xt
     return gather_shards(xt, B, group)

@@ -181,6 +181,12 @@ int cnb_edm_coeffs(const float* sigma, int B, float sigma_data, float sigma_min,
 /* out[b, i] = a[b] * x[b, i] (+ c[b] * y[b, i] if y != NULL); per-sample scalars (consistency :92, :132). */
 int cnb_scale_rows(const float* a, const float* x, const float* c, const float* y, float* out, int B,
                    long long per_sample, cnb_stream_t stream);
+/* Teacher-side x0 from a noise prediction with per-sample timesteps (distribution_matching_controlnet.py:191-216,
+ * consistency_controlnet_distilled.py:201-228): out = clamp((xt - sqrt_one_minus[t_b] * eps) / sqrt_alpha[t_b], -1, 1);
+ * t holds t_count in {1, B} int64 indices < num_timesteps into the two scheduler tables (device fp32). */
+int cnb_x0_from_eps(const float* xt, const float* eps, const float* sqrt_one_minus, const float* sqrt_alpha,
+                    const int64_t* t, int t_count, int num_timesteps, float* out, int B, long long per_sample,
+                    cnb_stream_t stream);
 
 /* layout plumbing between the reference's NCHW tensors and the channels-last workspace */
 int cnb_nchw_to_nhwc(const float* src, float* dst, int B, int C, int HW, int ldo, int out_coff, cnb_stream_t stream);

@@ -373,6 +373,29 @@ class SchedulerOracle:
         return mean + sigma * z, x0
 
 
+def teacher_x0(sd, cfg, sched, x_t, t, hint, prefix="teacher."):
+    """distribution_matching_controlnet.py:191-216 / consistency_controlnet_distilled.py:201-228: the DDPM ControlNet
+    teacher's noise prediction converted to a clamped x_0 with per-sample t."""
+    tsd = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+    t = torch.as_tensor(t).long()
+    if t.dim() == 0:
+        t = t.unsqueeze(0)
+    eps = controlnet_ddpm_forward(tsd, cfg, x_t, t, hint)
+    B = x_t.shape[0]
+    s1 = sched.sqrt_one_minus_alpha_cum_prod[t].reshape(B, 1, 1, 1)
+    s2 = sched.sqrt_alpha_cum_prod[t].reshape(B, 1, 1, 1)
+    return torch.clamp((x_t - s1 * eps) / s2, -1., 1.)
+
+
+def sigma_to_timestep(sched, sigma):
+    """consistency_controlnet_distilled.py:230-257 with the teacher's schedule."""
+    sigma = torch.as_tensor(sigma, dtype=torch.float32)
+    if sigma.dim() == 0:
+        sigma = sigma.unsqueeze(0)
+    schedule = torch.sqrt((1 - sched.alpha_cum_prod) / sched.alpha_cum_prod)
+    return torch.argmin(torch.abs(schedule.unsqueeze(0) - sigma.unsqueeze(-1)), dim=-1).long().clamp(0, 999)
+
+
 def ddpm_sample(forward_fn, sched, x_T, hint, steps, zs):
     """The loop of tools/sample_ddpm_controlnet.py:43-51 for t = steps-1 .. 0, with the
     per-step z injected: zs[k] is used at the k-th iteration (none at t == 0)."""

@@ -72,6 +72,31 @@ def trajectory(model, sched, x, hint, steps, name):
 
 
 @torch.no_grad()
+def make_teachers():
+    """Teacher-side inference of the distillation wrappers: get_teacher_prediction with per-sample t
+    and get_ddpm_teacher_prediction / sigma_to_timestep; the teacher checkpoint is a det_state_dict ControlNet."""
+    import tempfile
+    from models.distribution_matching_controlnet import DistributionMatchingControlNetDistilled as RefDMD
+    from models.consistency_controlnet_distilled import ConsistencyControlNetDistilled as RefConsD
+    cfg = syn.TINY_PARAMS
+    teacher = fill(RefControlNet(cfg), seed=3)
+    with tempfile.TemporaryDirectory() as d:
+        ck = os.path.join(d, "teacher.pth")
+        torch.save(teacher.state_dict(), ck)
+        dm = RefDMD(cfg, ck, device=torch.device("cpu")).eval()
+        cs = RefConsD(cfg, ck, device=torch.device("cpu")).eval()
+    x, hint = inputs("teacher_tiny", 3, cfg["im_channels"], cfg["im_size"])
+    t = torch.tensor([999, 412, 3])
+    sig = torch.tensor([60.0, 2.5, 0.05])
+    rec = {"dm_x0": dm.get_teacher_prediction(x, t, hint).numpy(),
+           "dm_x0_shared_t": dm.get_teacher_prediction(x[:1], torch.tensor(77), hint[:1]).numpy(),
+           "cs_t": cs.sigma_to_timestep(sig).numpy(),
+           "cs_x0": cs.get_ddpm_teacher_prediction(x, sig, hint).numpy()}
+    np.savez_compressed(os.path.join(OUT, "teachers_tiny.npz"), **rec)
+    print("teachers", {k: v.shape for k, v in rec.items()})
+
+
+@torch.no_grad()
 def make_vae():
     """models/vae.py decode / encode on the tiny VAE (decoder MidBlock + attention UpBlock) and, at batch 1, on the
     CelebHQ autoencoder_params (config/celebhq.yaml:27-38): output statistics + a strided sample of the image."""
@@ -109,6 +134,8 @@ def main():
     torch.manual_seed(0)
     if "--only-vae" in sys.argv:
         return make_vae()
+    if "--only-teachers" in sys.argv:
+        return make_teachers()
 
     # ---- DDPM ControlNet: tiny / mnist / cifar
     for name, cfg, B, ts in (("tiny", syn.TINY_PARAMS, 2, (999, 37, 0)),
@@ -199,6 +226,7 @@ def main():
     with open(os.path.join(OUT, "state_dict_manifest.json"), "w") as f:
         json.dump(man, f)
     make_vae()
+    make_teachers()
     print("done ->", OUT)
 
 

@@ -210,3 +210,73 @@ def test_vae_vs_reference_golden(rt):
         assert tuple(img.shape) == (1, 3, 128, 128)
         assert rel_l2(img[:, :, ::4, ::4].cpu(), gb["dec_strided"]) < TOL[mode], mode
     assert rt.lib().cnb_tc_error_flag() == 0
+
+
+def test_ldm_sampler_with_vae_decode_vs_oracle(rt):
+    """tools/sample_ldm_controlnet.py flow on the tiny LDM ControlNet + tiny VAE: injected-noise loop and decode of
+    the final latents against the oracle (cn_oracle.ddpm_sample + vae_decode); graph replay == eager with Philox."""
+    import cn_oracle as O
+    cfg, vcfg = syn.TINY_LDM_PARAMS, syn.TINY_VAE_PARAMS
+    m = _fill(_mod("models.controlnet_ldm").ControlNet(4, cfg, down_sample_factor=8))
+    vae = _fill(_mod("models.vae").VAE(3, vcfg), seed=1)
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    vsd = {k: v.cpu() for k, v in vae.state_dict().items()}
+    x, hint = inputs("ldm_vae", 2, 4, 8, hint_size=64, p=0.05)
+    sched = _mod("scheduler.linear_noise_scheduler").LinearNoiseScheduler(ldm_scheduler=True, **syn.CELEBHQ_DIFFUSION)
+    steps = 4
+    zs = [syn.det_noise(f"ldm_vae:z{k}", tuple(x.shape)) for k in range(steps)]
+    with torch.no_grad():
+        so = O.SchedulerOracle(ldm_scheduler=True, **syn.CELEBHQ_DIFFUSION)
+        xt_ref, _ = O.ddpm_sample(lambda a, t, h: O.controlnet_ldm_forward(sd, cfg, a, t, h), so, x, hint, steps, zs)
+        want = (torch.clamp(O.vae_decode(vsd, vcfg, xt_ref), -1., 1.) + 1) / 2
+    S = _mod("sampler")
+    for mode in _modes(rt):
+        rt.set_mode(mode)
+        smp = S.LDMSampler(m, sched, vae, seed=5, use_graph=False)
+        ims, lat = smp.sample_images(x.cuda(), hint.cuda(), steps=steps, zs=zs)
+        assert tuple(ims.shape) == (2, 3, 32, 32)
+        assert rel_l2(lat.cpu(), xt_ref) < TRAJ_TOL[mode], mode
+        assert rel_l2(ims.cpu(), want) < TRAJ_TOL[mode], mode
+    rt.set_mode("tf32" if rt.lib().cnb_has_tcgen05() else "fp32")
+    hc = hint.cuda()
+    eager = S.LDMSampler(m, sched, vae, seed=5, use_graph=False).sample_images(x.cuda(), hc, steps=steps)[0]
+    graph = S.LDMSampler(m, sched, vae, seed=5, use_graph=True, decode_chunk=1).sample_images(x.cuda(), hc, steps=steps)[0]
+    assert torch.equal(eager, graph)
+    assert rt.lib().cnb_tc_error_flag() == 0
+
+
+def test_teacher_predictions_vs_reference_golden(rt, tmp_path):
+    """Teacher-side inference of the distillation wrappers on the GPU kernels: per-sample t, the
+    x0 conversion kernel (bit-exact op order), sigma -> timestep lookup."""
+    cfg = syn.TINY_PARAMS
+    teacher = _mod("models.controlnet").ControlNet(cfg)
+    teacher.load_state_dict(syn.det_state_dict(teacher.state_dict(), 3))
+    ck = os.path.join(str(tmp_path), "teacher.pth")
+    torch.save(teacher.state_dict(), ck)
+    dm = _mod("models.distribution_matching_controlnet").DistributionMatchingControlNetDistilled(cfg, ck, device="cuda").cuda().eval()
+    cs = _mod("models.consistency_controlnet_distilled").ConsistencyControlNetDistilled(cfg, ck, device="cuda").cuda().eval()
+    g = golden("teachers_tiny")
+    x, hint = inputs("teacher_tiny", 3, cfg["im_channels"], cfg["im_size"])
+    xc, hc = x.cuda(), hint.cuda()
+    sig = torch.tensor([60.0, 2.5, 0.05]).cuda()
+    assert cs.sigma_to_timestep(sig).cpu().tolist() == g["cs_t"].tolist()
+    for mode in _modes(rt):
+        rt.set_mode(mode)
+        a = dm.get_teacher_prediction(xc, torch.tensor([999, 412, 3]).cuda(), hc)
+        b = dm.get_teacher_prediction(xc[:1].contiguous(), torch.tensor(77), hc[:1].contiguous())
+        c = cs.get_ddpm_teacher_prediction(xc, sig, hc)
+        assert rel_l2(a.cpu(), g["dm_x0"]) < TOL[mode], mode
+        assert rel_l2(b.cpu(), g["dm_x0_shared_t"]) < TOL[mode], mode
+        assert rel_l2(c.cpu(), g["cs_x0"]) < TOL[mode], mode
+    with pytest.raises(ValueError):
+        _mod("models.consistency_controlnet_distilled").ConsistencyControlNetDistilled(cfg).get_ddpm_teacher_prediction(xc, sig, hc)
+    # the conversion kernel alone is bit-exact against the reference expression
+    eps = syn.det_noise("teacher_tiny:eps", tuple(x.shape))
+    sch = dm.teacher_scheduler
+    t = torch.tensor([5, 500, 998])
+    s1 = sch.sqrt_one_minus_alpha_cum_prod[t].reshape(3, 1, 1, 1)
+    s2 = sch.sqrt_alpha_cum_prod[t].reshape(3, 1, 1, 1)
+    want = torch.clamp((x - s1 * eps) / s2, -1., 1.)
+    ops = _mod("ops")
+    got = ops.x0_from_eps(xc, eps.cuda(), sch.sqrt_one_minus_alpha_cum_prod.cuda(), sch.sqrt_alpha_cum_prod.cuda(), t.cuda())
+    assert torch.equal(got.cpu(), want)

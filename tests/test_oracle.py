@@ -155,3 +155,35 @@ def test_vae_celebhq_decode_vs_golden():
     assert tuple(img.shape) == (1, 3, 128, 128)
     assert rel_l2(img[:, :, ::4, ::4], g["dec_strided"]) < 5e-6
     assert abs(float(img.double().pow(2).sum()) / float(g["dec_sqsum"]) - 1) < 1e-5
+
+
+def _teacher_wrappers(tmp_path):
+    """Product wrappers (CPU parameter holders) built from a det_state_dict ControlNet checkpoint, as make_golden does."""
+    cfg = syn.TINY_PARAMS
+    CN = importlib.import_module("controlnet-pytorch_b200.models.controlnet").ControlNet
+    teacher = CN(cfg)
+    teacher.load_state_dict(syn.det_state_dict(teacher.state_dict(), 3))
+    ck = os.path.join(str(tmp_path), "teacher.pth")
+    torch.save(teacher.state_dict(), ck)
+    dm = importlib.import_module("controlnet-pytorch_b200.models.distribution_matching_controlnet")
+    cs = importlib.import_module("controlnet-pytorch_b200.models.consistency_controlnet_distilled")
+    return (cfg, dm.DistributionMatchingControlNetDistilled(cfg, ck, device=torch.device("cpu")),
+            cs.ConsistencyControlNetDistilled(cfg, ck, device=torch.device("cpu")))
+
+
+def test_teacher_predictions_vs_golden(tmp_path):
+    """get_teacher_prediction / get_ddpm_teacher_prediction / sigma_to_timestep."""
+    cfg, dm, cs = _teacher_wrappers(tmp_path)
+    g = golden("teachers_tiny")
+    x, hint = inputs("teacher_tiny", 3, cfg["im_channels"], cfg["im_size"])
+    so = O.SchedulerOracle(**syn.MNIST_DIFFUSION)
+    sig = torch.tensor([60.0, 2.5, 0.05])
+    with torch.no_grad():
+        a = O.teacher_x0(dm.state_dict(), cfg, so, x, torch.tensor([999, 412, 3]), hint, prefix="teacher.")
+        b = O.teacher_x0(dm.state_dict(), cfg, so, x[:1], torch.tensor(77), hint[:1], prefix="teacher.")
+        t = O.sigma_to_timestep(so, sig)
+        c = O.teacher_x0(cs.state_dict(), cfg, so, x, t, hint, prefix="ddpm_teacher.")
+    assert rel_l2(a, g["dm_x0"]) < TOL and rel_l2(b, g["dm_x0_shared_t"]) < TOL
+    assert t.tolist() == g["cs_t"].tolist()
+    assert cs.sigma_to_timestep(sig).tolist() == g["cs_t"].tolist()     # host-side table lookup of the product class
+    assert rel_l2(c, g["cs_x0"]) < TOL
