@@ -126,6 +126,8 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
   for (int i = 0; i < NV; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float lsum[4] = {0.f, 0.f, 0.f, 0.f};          // [0] = denominator of row g, [2] = of row g + 8
   float m0 = -INFINITY, m1 = -INFINITY;
+  float ms0 = 0.f, ms1 = 0.f;                    // m * scale_log2 of the current reference maxima
+  const float lazy = 8.0f / scale_log2;          // 2^8 headroom, in raw score units
 
   const int ntiles = (L + BK - 1) / BK;
   constexpr int CPR = D * 2 / CH;                // chunks per row
@@ -202,13 +204,17 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite: every tile has >= 1 valid key
-    const float cr0 = ex2((m0 - mn0) * scale_log2), cr1 = ex2((m1 - mn1) * scale_log2);
-    m0 = mn0; m1 = mn1;
-    const float ms0 = mn0 * scale_log2, ms1 = mn1 * scale_log2;
-    lsum[0] *= cr0; lsum[1] *= cr0; lsum[2] *= cr1; lsum[3] *= cr1;
+    // Lazy reference maximum: it only moves when a tile maximum exceeds it by more than 2^LAZY (P <= 2^LAZY is harmless
+    // in fp16, the sums are fp32), so after the first tiles the correction (2 MUFU + the O / l rescale) is skipped.
+    if (__any_sync(0xffffffffu, mx0 > m0 + lazy || mx1 > m1 + lazy)) {
+      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite: every tile has >= 1 valid key
+      const float cr0 = ex2((m0 - mn0) * scale_log2), cr1 = ex2((m1 - mn1) * scale_log2);
+      m0 = mn0; m1 = mn1;
+      ms0 = mn0 * scale_log2; ms1 = mn1 * scale_log2;
+      lsum[0] *= cr0; lsum[1] *= cr0; lsum[2] *= cr1; lsum[3] *= cr1;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) { o[i][0] *= cr0; o[i][1] *= cr0; o[i][2] *= cr1; o[i][3] *= cr1; }
+      for (int i = 0; i < NV; ++i) { o[i][0] *= cr0; o[i][1] *= cr0; o[i][2] *= cr1; o[i][3] *= cr1; }
+    }
     // ---- P = exp2(.) packed to fp16 = A fragments of the second MMA;  O += P V,  l += P 1
 #pragma unroll
     for (int kk = 0; kk < NG; ++kk) {

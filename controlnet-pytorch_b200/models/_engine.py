@@ -369,13 +369,41 @@ def conv_in(unet, x_nhwc, mode, residual=None):
     return conv16(x_nhwc, ci.weight, "3x3", ci.out_channels, mode, bias=raw(ci.bias), residual=residual)
 
 
+def gn_silu_conv_tail(norm, conv, h, mode):
+    """GroupNorm -> SiLU -> 3x3 conv to a handful of channels (U-Net conv_out, VAE decoder / encoder conv_out).
+    Returns the NHWC result, possibly as a channel-narrowed VIEW of a wider buffer (ops.nhwc_to_nchw reads strides).
+    Narrow inputs (MNIST / CIFAR: 16 channels) run the exact direct FFMA kernel on fp16 activations.  Wide inputs
+    (CelebHQ U-Net 128 -> 4, VAE decoder 128 -> 3 at 128x128: 3.5 k MACs per pixel) run on the tensor core with Cout
+    zero-padded to 16: 4-5x wasted MMA work is still ~10x faster than FFMA."""
+    cout, cin = conv.out_channels, conv.in_channels
+    lowp = mode != rt.MODE_F32 and _F16_ENABLED and cout <= 4
+    tc = lowp and cin % 16 == 0 and cin >= 64
+    h16 = lowp and cin % 4 == 0
+    h = ops.groupnorm(h, raw(norm.weight), raw(norm.bias), norm.num_groups, silu=True, out_f16=h16)
+    if not tc:
+        return ops.conv(h, packed_conv(conv.weight, mode), "3x3", cout, bias=raw(conv.bias), mode=mode)
+
+    def build():
+        w = torch.zeros((16,) + tuple(conv.weight.shape[1:]), device=conv.weight.device, dtype=torch.float32)
+        w[:cout] = conv.weight.detach()
+        b = torch.zeros(16, device=conv.weight.device, dtype=torch.float32)
+        b[:cout] = conv.bias.detach()
+        packed = ops.pack_conv_weight(w, False)
+        return packed, ops.cast_f16(packed), b
+    store = conv.weight.__dict__.setdefault("_cnb_pack", {})
+    stamp = (conv.weight._version, conv.weight.data_ptr(), conv.bias._version, conv.bias.data_ptr())
+    ent = store.get(("pad16",))
+    if ent is None or ent[0] != stamp:
+        with torch.no_grad():
+            ent = (stamp, build())
+        store[("pad16",)] = ent
+    packed, packed16, bias = ent[1]
+    return ops.conv(h, packed, "3x3", 16, bias=bias, mode=mode, weight_lp=packed16, out_f16=True)[..., :cout]
+
+
 def conv_out(unet, x, mode):
-    co = unet.conv_out
-    # the direct small-Cout kernel reads fp16 activations in the tensor-core modes (half the bytes of this HBM-bound tail)
-    h16 = mode != rt.MODE_F32 and _F16_ENABLED and co.out_channels <= 4 and co.in_channels % 4 == 0
-    h = ops.groupnorm(x, raw(unet.norm_out.weight), raw(unet.norm_out.bias), unet.norm_out.num_groups, silu=True,
-                      out_f16=h16)
-    return ops.conv(h, packed_conv(co.weight, mode), "3x3", co.out_channels, bias=raw(co.bias), mode=mode)
+    """norm_out -> SiLU -> conv_out (unet_base.py:371-373)."""
+    return gn_silu_conv_tail(unet.norm_out, unet.conv_out, x, mode)
 
 
 def run_unet_body(unet, h, plan, mode):

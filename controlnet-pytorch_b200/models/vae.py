@@ -62,37 +62,6 @@ class VAE(nn.Module):
     def _conv(conv, h, kind, mode):
         return E.conv16(h, conv.weight, kind, conv.out_channels, mode, bias=E.raw(conv.bias))
 
-    @staticmethod
-    def _tail(norm, conv, h, mode):
-        """GroupNorm -> SiLU -> 3x3 conv to a handful of channels; returns (nhwc tensor, valid channels).
-        Wide inputs (decoder_conv_out: 128 -> 3 at 128x128 is 3.5 k MACs per pixel) run on the tensor core with Cout
-        zero-padded to 16 -- 5x wasted MMA work is still 10x faster than the direct FFMA kernel, which is meant for
-        the 16-channel U-Net tails; narrow ones keep the exact direct kernel."""
-        cout, cin = conv.out_channels, conv.in_channels
-        tc = mode != rt.MODE_F32 and E._F16_ENABLED and cout <= 4 and cin % 16 == 0 and cin >= 64
-        h16 = mode != rt.MODE_F32 and E._F16_ENABLED and cout <= 4 and cin % 4 == 0
-        h = ops.groupnorm(h, E.raw(norm.weight), E.raw(norm.bias), norm.num_groups, silu=True, out_f16=h16)
-        if tc:
-            def build():
-                w = torch.zeros((16,) + tuple(conv.weight.shape[1:]), device=conv.weight.device, dtype=torch.float32)
-                w[:cout] = conv.weight.detach()
-                b = torch.zeros(16, device=conv.weight.device, dtype=torch.float32)
-                b[:cout] = conv.bias.detach()
-                packed = ops.pack_conv_weight(w, False)
-                return packed, ops.cast_f16(packed), b
-            stamp_holder = conv.weight
-            store = stamp_holder.__dict__.setdefault("_cnb_pack", {})
-            stamp = (conv.weight._version, conv.weight.data_ptr(), conv.bias._version, conv.bias.data_ptr())
-            ent = store.get(("pad16",))
-            if ent is None or ent[0] != stamp:
-                with torch.no_grad():
-                    ent = (stamp, build())
-                store[("pad16",)] = ent
-            packed, packed16, bias = ent[1]
-            return ops.conv(h, packed, "3x3", 16, bias=bias, mode=mode, weight_lp=packed16, out_f16=True), cout
-        return ops.conv(h, E.packed_conv(conv.weight, mode), "3x3", cout, bias=E.raw(conv.bias), mode=mode,
-                        out_f16=False), cout
-
     def _decode_nhwc(self, z_nhwc, mode):
         h = self._conv(self.post_quant_conv, z_nhwc, "1x1", mode)
         h = self._conv(self.decoder_conv_in, h, "3x3", mode)
@@ -100,12 +69,11 @@ class VAE(nn.Module):
             h = E.run_mid(mid, h, None, mode)
         for up in self.decoder_layers:
             h = E.run_up(up, h, None, None, mode)
-        return self._tail(self.decoder_norm_out, self.decoder_conv_out, h, mode)
+        return E.gn_silu_conv_tail(self.decoder_norm_out, self.decoder_conv_out, h, mode)
 
     def decode(self, z):
         mode = rt.get_mode()
-        h, c = self._decode_nhwc(ops.nchw_to_nhwc(E._check_x(z)), mode)
-        return ops.nhwc_to_nchw(h, c=c)
+        return ops.nhwc_to_nchw(self._decode_nhwc(ops.nchw_to_nhwc(E._check_x(z)), mode))
 
     def _encode_out(self, x, mode):
         h = self._conv(self.encoder_conv_in, ops.nchw_to_nhwc(E._check_x(x)), "3x3", mode)
@@ -113,7 +81,7 @@ class VAE(nn.Module):
             h = E.run_down(down, h, None, mode)
         for mid in self.encoder_mids:
             h = E.run_mid(mid, h, None, mode)
-        h, _ = self._tail(self.encoder_norm_out, self.encoder_conv_out, h, mode)
+        h = E.gn_silu_conv_tail(self.encoder_norm_out, self.encoder_conv_out, h, mode)
         h = ops.conv(h, E.packed_conv(self.pre_quant_conv.weight, mode), "1x1", self.pre_quant_conv.out_channels,
                      bias=E.raw(self.pre_quant_conv.bias), mode=mode, out_f16=False)
         return ops.nhwc_to_nchw(h)

@@ -174,9 +174,13 @@ def nchw_to_nhwc(x, out=None, out_coff=0):
 
 
 def nhwc_to_nchw(x, in_coff=0, c=None):
+    """x: (B, H, W, C) channels-last, contiguous or a channel-narrowed view of a wider contiguous buffer."""
     rt.require_cuda(x)
-    B, H, W, ld = x.shape
-    c = ld - in_coff if c is None else c
+    B, H, W, cv = x.shape
+    ld = x.stride(2)
+    if x.stride(3) != 1 or x.stride(1) != W * ld or x.stride(0) != H * W * ld or ld < cv:
+        raise rt.CnbError("nhwc_to_nchw: expected a channels-last tensor or a channel slice of one")
+    c = cv - in_coff if c is None else c
     if c == 1 and ld == 1 and x.dtype == torch.float32:
         return x.reshape(B, 1, H, W)
     out = torch.empty((B, c, H, W), device=x.device, dtype=torch.float32)
