@@ -57,6 +57,7 @@ struct alignas(64) TmaArgs {
   int bres;         // 1 = the whole packed weight tile stays resident in smem, the ring carries A stages only
   int s_run;        // ring depth actually used (<= Cfg::S)
   int ring_off, stage_bytes, epi_off, bar_off;
+  int epi_alt;      // 1 = the two epilogue warp groups alternate TILES (short-K layers), 0 = they split a tile's columns
   uint32_t tap_off[CNB_MAX_TAPS];   // offset_w | offset_h << 16
 };
 
@@ -155,7 +156,7 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], EPI_WARPS);
+      mbar_init(&tempty_bar[i], a.epi_alt ? EPI_WARPS / 2 : EPI_WARPS);
     }
     mbar_init(bres_bar, 1);
     *abort_flag = 0;
@@ -308,7 +309,10 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
     tc_fence_before();
   } else {
     // ============================ epilogue (warps 2..9) ============================
-    // Two warps share each TMEM lane quarter (q = warp % 4) and split the accumulator's column slabs by parity.
+    // Two warps share each TMEM lane quarter (q = warp % 4).  Long-K layers: they split the accumulator's column slabs by
+    // parity.  Short-K layers (epi_alt): a tile's MMAs take a few hundred cycles while its epilogue is a ~2-3 k cycle
+    // latency chain (barrier wake-up, tcgen05.ld, smem transpose, residual loads, stores), so the two warp groups take
+    // alternate TILES (= alternate TMEM accumulators) and two epilogues are in flight at once.
     // With one warp per scheduler the epilogue is instruction-latency bound, so the dense variants (EPI 0..2) keep
     // the per-row work to LDS.128 (+LDG.128 residual) + 4 FADD + STG and fully unroll it.
     const int ew = warp - 2;
@@ -323,7 +327,10 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
     const float* bias = a.bias;
     const float* temb_row = (a.temb && !a.temb_per_sample) ? a.temb : nullptr;
     int tcount = 0;
+    const bool alt = a.epi_alt != 0;
+    const int si0 = alt ? 0 : par, sstep = alt ? 1 : 2;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      if (alt && (tcount & 1) != par) continue;               // the other warp group owns this accumulator
       const int mt = tile / tiles_n, nt = tile - mt * tiles_n;
       const int m_w = mt * BM + q * 32;                       // first GEMM row of this warp
       const int n0 = nt * BN;
@@ -357,18 +364,18 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
       if (!mbar_wait(&tfull_bar[acc], (uint32_t)((tcount >> 1) & 1), abort_flag)) break;
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)(acc * C::ACC_STRIDE) + ((uint32_t)(q * 32) << 16);
-      if (par >= NSLAB) {                                     // single-slab tiles: the odd warps have nothing to read
+      if (!alt && par >= NSLAB) {                             // single-slab tiles: the odd warps have nothing to read
         tc_fence_before();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
 #pragma unroll 1
-      for (int si = par; si < NSLAB; si += 2) {
+      for (int si = si0; si < NSLAB; si += sstep) {
         const int c0 = si * SLAB;
         uint32_t r[SLAB];
 #pragma unroll
         for (int j = 0; j < SLAB / 16; ++j) tmem_ld16_nowait(t_addr + (uint32_t)(c0 + 16 * j), r + 16 * j);
         tmem_ld_wait();
-        if (si + 2 >= NSLAB) {            // this warp's last slab: hand its share of the TMEM buffer back
+        if (si + sstep >= NSLAB) {        // this warp's last slab: hand its share of the TMEM buffer back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -537,6 +544,18 @@ static int launch_epi(const TmaArgs& a_in, int num_sms, cudaStream_t st) {
     a.epi_off = C::EPI_OFFSET;
   }
   a.bar_off = a.epi_off + C::EPI_BYTES;
+  {
+    // alternate-tile epilogue when a tile's tensor work (~BN * K / 32 cycles) is shorter than its epilogue
+    static int alt_env = -2;
+    if (alt_env == -2) {
+      const char* e = getenv("CNB_CONV_EPI_ALT");
+      alt_env = e ? atoi(e) : -1;
+    }
+    const long long ktot = (long long)nkb * (RB / (HALF ? 2 : 4));   // nkb counts every (tap, chunk) block
+    // measured (B = 1024): halo 3x3 16->16 @28 54 -> 44 us, 64->64 @28 97 -> 91, 32->64 @28 89 -> 83; dense 1x1 layers
+    // with several column slabs lose (256->768 @7 40 -> 44 us), so only the halo layers switch
+    a.epi_alt = alt_env >= 0 ? alt_env : ((a.halo && (long long)BN * ktot < 131072) ? 1 : 0);
+  }
   smem_bytes = (size_t)a.bar_off + C::BAR_BYTES + 1024;
   CNB_CUDA(launch_pdl(conv_tma_kernel<BN, HALF, EPI, RB>, dim3(grid), dim3(NUM_THREADS), smem_bytes, st, a));
   CNB_LAUNCH_CHECK();
