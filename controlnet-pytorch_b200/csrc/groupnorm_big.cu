@@ -2,7 +2,8 @@
 // 8 MB per sample; CelebHQ-latent students: 32x32x256 = 512 KB).  The one-CTA-per-sample kernels of groupnorm.cu then
 // sweep the slab three times from L2 / HBM with B CTAs on 148 SMs; here a sample is split over S row ranges:
 //
-//   stats kernel   grid (S, B): each CTA streams its rows ONCE with 16-byte loads (thread <-> 8 fixed channels) and
+//   stats kernel   grid (S, B): each CTA streams its rows ONCE with 16-byte loads (default caching: the apply kernel's
+//                  re-read hits L2 when B * slab fits; the apply kernel reads evict-first) (thread <-> 8 fixed channels) and
 //                  accumulates shifted sums  sum(x - p), sum((x - p)^2)  per channel, p = the channel's value in the
 //                  CTA's first row (no cancellation: |mean - p| ~ sigma); per-channel (n, mean, M2) are merged per
 //                  group with Chan's parallel-variance formula and written as one float4 per (sample, range, group)
@@ -65,9 +66,25 @@ stats_kernel(const __half* __restrict__ x, float4* __restrict__ partial, int HW,
   if (r0 < R && nrows > 0) {
     widen8(__ldg(xs + col), piv);
     int row = r0;
-    // two rows in flight per iteration
+    // four rows (64 bytes per thread) in flight per iteration: ~60 KB per SM, what HBM latency x bandwidth needs
+    for (; row + 3 * R < nrows; row += 4 * R) {
+      uint4 raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) raw[u] = __ldg(xs + (size_t)(row + u * R) * C8 + col);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[8];
+        widen8(raw[u], v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = v[i] - piv[i];
+          sum[i] += d;
+          sq[i] = fmaf(d, d, sq[i]);
+        }
+      }
+    }
     for (; row + R < nrows; row += 2 * R) {
-      const uint4 a = __ldcs(xs + (size_t)row * C8 + col), c = __ldcs(xs + (size_t)(row + R) * C8 + col);
+      const uint4 a = __ldg(xs + (size_t)row * C8 + col), c = __ldg(xs + (size_t)(row + R) * C8 + col);
       float va[8], vc[8];
       widen8(a, va);
       widen8(c, vc);
@@ -80,7 +97,7 @@ stats_kernel(const __half* __restrict__ x, float4* __restrict__ partial, int HW,
     }
     if (row < nrows) {
       float va[8];
-      widen8(__ldcs(xs + (size_t)row * C8 + col), va);
+      widen8(__ldg(xs + (size_t)row * C8 + col), va);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float da = va[i] - piv[i];
@@ -153,9 +170,9 @@ apply_kernel(const __half* __restrict__ x, void* __restrict__ y, const float4* _
   const int row0 = s * rows_per_cta;
   const int nrows = max(0, min(rows_per_cta, HW - row0));
   const uint4* xs = reinterpret_cast<const uint4*>(x) + ((size_t)b * HW + row0) * C8;
-  for (int row = r0; row < nrows; row += R) {
+  auto emit = [&](const uint4& raw, int row) {
     float v[8];
-    widen8(__ldcs(xs + (size_t)row * C8 + col), v);
+    widen8(raw, v);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       v[i] = fmaf(v[i], sc[i], sh[i]);
@@ -173,7 +190,16 @@ apply_kernel(const __half* __restrict__ x, void* __restrict__ y, const float4* _
       yo[0] = make_float4(v[0], v[1], v[2], v[3]);
       yo[1] = make_float4(v[4], v[5], v[6], v[7]);
     }
+  };
+  int row = r0;
+  for (; row + 3 * R < nrows; row += 4 * R) {                // four 16-byte loads in flight per thread
+    uint4 raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) raw[u] = __ldcs(xs + (size_t)(row + u * R) * C8 + col);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) emit(raw[u], row + u * R);
   }
+  for (; row < nrows; row += R) emit(__ldcs(xs + (size_t)row * C8 + col), row);
 }
 
 // row ranges per sample: enough CTAs to fill the GPU ~8 deep, at least 4 sweeps of rows per CTA
