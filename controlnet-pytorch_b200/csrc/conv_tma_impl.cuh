@@ -221,9 +221,12 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
         const int oy = rem / a.OW;
         const int ox = rem - oy * a.OW;
         const int w0 = ox * a.stride + a.lower_w, h0 = oy * a.stride + a.lower_h;
-        for (int tap = 0; tap < a.ntaps && ok; ++tap) {
-          const uint32_t off = a.tap_off[tap];
-          for (int kc = 0; kc < a.kchunks; ++kc) {
+        // K is walked chunk-major (channel chunk outer, tap inner) -- the same order as the halo mode, so the fp32
+        // accumulation sequence of every output element, and with it the result, does not depend on which of the two
+        // plans the batch size selects (batch / shard invariance, tests/test_models_gpu.py)
+        for (int kc = 0; kc < a.kchunks && ok; ++kc) {
+          for (int tap = 0; tap < a.ntaps; ++tap) {
+            const uint32_t off = a.tap_off[tap];
             const uint32_t sa = stage_begin();
             if (!ok) break;
             tma_load_im2col_4d(sa, &a.map_a, &full_bar[s], kc * KC, w0, h0, b, (uint16_t)(off & 0xffffu),
@@ -288,13 +291,16 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
           if (++s == s_run) { s = 0; ++round; }
         }
       } else
-      for (int kb = 0; kb < nkb && ok; ++kb) {
+      for (int kb = 0, tap = 0, kc = 0; kb < nkb && ok; ++kb) {
         ok = mbar_wait(&full_bar[s], (uint32_t)(round & 1), abort_flag);
         tc_fence_after();
+        // stages arrive chunk-major (kc outer, tap inner); the resident weight blocks are stored tap-major
+        const int bidx = kb < a.ntaps * a.kchunks ? tap * a.kchunks + kc : kb;
+        if (++tap == a.ntaps) { tap = 0; ++kc; }
         if (lane == 0 && ok) {
           const uint32_t a_addr = ring_base + (uint32_t)s * stage_bytes;
           const uint64_t adesc = make_desc_kmajor<RB>(a_addr);
-          const uint64_t bdesc = make_desc_kmajor<RB>(bres ? smem_base + (uint32_t)(kb * C::B_STAGE_BYTES)
+          const uint64_t bdesc = make_desc_kmajor<RB>(bres ? smem_base + (uint32_t)(bidx * C::B_STAGE_BYTES)
                                                            : a_addr + A_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < RB / 32; ++k)

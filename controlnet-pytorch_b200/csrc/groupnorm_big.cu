@@ -5,8 +5,9 @@
 //   stats kernel   grid (S, B): each CTA streams its rows ONCE with 16-byte loads (default caching: the apply kernel's
 //                  re-read hits L2 when B * slab fits; the apply kernel reads evict-first) (thread <-> 8 fixed channels) and
 //                  accumulates shifted sums  sum(x - p), sum((x - p)^2)  per channel, p = the channel's value in the
-//                  CTA's first row (no cancellation: |mean - p| ~ sigma); per-channel (n, mean, M2) are merged per
-//                  group with Chan's parallel-variance formula and written as one float4 per (sample, range, group)
+//                  block's first row (no cancellation: |mean - p| ~ sigma); per-channel (n, mean, M2) are merged per
+//                  group with Chan's parallel-variance formula, blocks are merged in double and written as three
+//                  doubles per (sample, range, group)
 //   apply kernel   grid (S, B): merges the S partials of its sample (Chan again, double accumulators), folds gamma /
 //                  beta into one FMA per element, applies SiLU (tanh form for fp16 outputs) and stores 16 bytes
 //
@@ -48,8 +49,13 @@ __device__ __forceinline__ void chan_merge(T& n, T& mean, T& m2, T nb, T mb, T m
   n = nt;
 }
 
+// Statistics are computed on FIXED blocks of BLK_SWEEPS * R rows (fp32, deterministic per block) and merged in double,
+// so the result does not depend on how many row ranges S a sample is split into (S follows the batch size): GroupNorm
+// stays batch / shard invariant like the one-CTA-per-sample kernels.
+constexpr int BLK_SWEEPS = 16;
+
 __global__ void __launch_bounds__(NT)
-stats_kernel(const __half* __restrict__ x, float4* __restrict__ partial, int HW, int C, int G, int rows_per_cta) {
+stats_kernel(const __half* __restrict__ x, double* __restrict__ partial, int HW, int C, int G, int rows_per_cta) {
   extern __shared__ float sm[];
   const int C8 = C >> 3;
   const int R = NT / C8;                       // pixel rows per sweep
@@ -57,24 +63,41 @@ stats_kernel(const __half* __restrict__ x, float4* __restrict__ partial, int HW,
   float* cstat = part + (size_t)R * C * 2;     // [C][2]     per-channel mean, M2
   const int tid = threadIdx.x, col = tid % C8, r0 = tid / C8;
   const int S = gridDim.x, s = blockIdx.x, b = blockIdx.y;
-  const int row0 = s * rows_per_cta;
-  const int nrows = max(0, min(rows_per_cta, HW - row0));
-  const uint4* xs = reinterpret_cast<const uint4*>(x) + ((size_t)b * HW + row0) * C8;
-  float piv[8], sum[8], sq[8];
+  const int cta_row0 = s * rows_per_cta;
+  const int cta_rows = max(0, min(rows_per_cta, HW - cta_row0));
+  const int BLK = BLK_SWEEPS * R;              // rows_per_cta is a multiple of BLK (host)
+  const int cg = C / G;
+  double gn = 0.0, gmean = 0.0, gm2 = 0.0;     // running merge of this CTA's blocks (threads g < G)
+  for (int blk0 = 0; blk0 < cta_rows; blk0 += BLK) {
+    const int row0 = cta_row0 + blk0;
+    const int nrows = min(BLK, cta_rows - blk0);
+    const uint4* xs = reinterpret_cast<const uint4*>(x) + ((size_t)b * HW + row0) * C8;
+    float piv[8], sum[8], sq[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { piv[i] = 0.f; sum[i] = 0.f; sq[i] = 0.f; }
-  if (r0 < R && nrows > 0) {
-    widen8(__ldg(xs + col), piv);
-    int row = r0;
-    // four rows (64 bytes per thread) in flight per iteration: ~60 KB per SM, what HBM latency x bandwidth needs
-    for (; row + 3 * R < nrows; row += 4 * R) {
-      uint4 raw[4];
+    for (int i = 0; i < 8; ++i) { piv[i] = 0.f; sum[i] = 0.f; sq[i] = 0.f; }
+    if (r0 < R) {
+      widen8(__ldg(xs + col), piv);
+      int row = r0;
+      // four rows (64 bytes per thread) in flight per iteration: ~60 KB per SM, what HBM latency x bandwidth needs
+      for (; row + 3 * R < nrows; row += 4 * R) {
+        uint4 raw[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) raw[u] = __ldg(xs + (size_t)(row + u * R) * C8 + col);
+        for (int u = 0; u < 4; ++u) raw[u] = __ldg(xs + (size_t)(row + u * R) * C8 + col);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 4; ++u) {
+          float v[8];
+          widen8(raw[u], v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float d = v[i] - piv[i];
+            sum[i] += d;
+            sq[i] = fmaf(d, d, sq[i]);
+          }
+        }
+      }
+      for (; row < nrows; row += R) {
         float v[8];
-        widen8(raw[u], v);
+        widen8(__ldg(xs + (size_t)row * C8 + col), v);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float d = v[i] - piv[i];
@@ -82,63 +105,42 @@ stats_kernel(const __half* __restrict__ x, float4* __restrict__ partial, int HW,
           sq[i] = fmaf(d, d, sq[i]);
         }
       }
-    }
-    for (; row + R < nrows; row += 2 * R) {
-      const uint4 a = __ldg(xs + (size_t)row * C8 + col), c = __ldg(xs + (size_t)(row + R) * C8 + col);
-      float va[8], vc[8];
-      widen8(a, va);
-      widen8(c, vc);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float da = va[i] - piv[i], dc = vc[i] - piv[i];
-        sum[i] += da + dc;
-        sq[i] = fmaf(da, da, fmaf(dc, dc, sq[i]));
+        part[((size_t)r0 * C + col * 8 + i) * 2] = sum[i];
+        part[((size_t)r0 * C + col * 8 + i) * 2 + 1] = sq[i];
       }
     }
-    if (row < nrows) {
-      float va[8];
-      widen8(__ldg(xs + (size_t)row * C8 + col), va);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float da = va[i] - piv[i];
-        sum[i] += da;
-        sq[i] = fmaf(da, da, sq[i]);
+    __syncthreads();
+    // per channel: row class r covers rows r, r + R, ... of the block; each class has its own count
+    for (int c = tid; c < C; c += NT) {
+      const float p = __half2float(x[((size_t)b * HW + row0) * C + c]);
+      float s1 = 0.f, s2 = 0.f;
+      for (int r = 0; r < R; ++r) {
+        s1 += part[((size_t)r * C + c) * 2];
+        s2 += part[((size_t)r * C + c) * 2 + 1];
       }
+      const float dm = s1 / (float)nrows;
+      cstat[2 * c] = p + dm;
+      cstat[2 * c + 1] = fmaxf(s2 - s1 * dm, 0.f);
     }
-  }
-  if (r0 < R) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      part[((size_t)r0 * C + col * 8 + i) * 2] = sum[i];
-      part[((size_t)r0 * C + col * 8 + i) * 2 + 1] = sq[i];
+    __syncthreads();
+    for (int g = tid; g < G; g += NT) {
+      float n = 0.f, mean = 0.f, m2 = 0.f;
+      for (int c = 0; c < cg; ++c) chan_merge(n, mean, m2, (float)nrows, cstat[2 * (g * cg + c)], cstat[2 * (g * cg + c) + 1]);
+      chan_merge(gn, gmean, gm2, (double)n, (double)mean, (double)m2);
     }
+    // (the next block's writes to part / cstat are ordered behind these reads by its own two barriers)
   }
-  __syncthreads();
-  // per channel: shifted sums over the R row classes -> (mean, M2) over the CTA's nrows rows
-  for (int c = tid; c < C; c += NT) {
-    float s1 = 0.f, s2 = 0.f;
-    for (int r = 0; r < R; ++r) {
-      s1 += part[((size_t)r * C + c) * 2];
-      s2 += part[((size_t)r * C + c) * 2 + 1];
-    }
-    const float p = nrows > 0 ? __half2float(x[((size_t)b * HW + row0) * C + c]) : 0.f;
-    const float n = (float)nrows;
-    const float dm = nrows > 0 ? s1 / n : 0.f;
-    cstat[2 * c] = p + dm;
-    cstat[2 * c + 1] = fmaxf(s2 - s1 * dm, 0.f);
-  }
-  __syncthreads();
-  const int cg = C / G;
-  for (int g = tid; g < G; g += NT) {
-    float n = 0.f, mean = 0.f, m2 = 0.f;
-    for (int c = 0; c < cg; ++c) chan_merge(n, mean, m2, (float)nrows, cstat[2 * (g * cg + c)], cstat[2 * (g * cg + c) + 1]);
-    partial[((size_t)b * S + s) * G + g] = make_float4(n, mean, m2, 0.f);
+  for (int g = tid; g < G; g += NT) {          // G <= NT: each thread owns at most one group
+    double* o = partial + (((size_t)b * S + s) * G + g) * 3;
+    o[0] = gn; o[1] = gmean; o[2] = gm2;
   }
 }
 
 template <bool SILU, bool HALF>
 __global__ void __launch_bounds__(NT)
-apply_kernel(const __half* __restrict__ x, void* __restrict__ y, const float4* __restrict__ partial,
+apply_kernel(const __half* __restrict__ x, void* __restrict__ y, const double* __restrict__ partial,
              const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C, int G, float eps,
              int rows_per_cta, int S_stats) {
   extern __shared__ float sm[];
@@ -151,8 +153,8 @@ apply_kernel(const __half* __restrict__ x, void* __restrict__ y, const float4* _
   for (int g = tid; g < G; g += NT) {
     double n = 0.0, mean = 0.0, m2 = 0.0;
     for (int q = 0; q < S_stats; ++q) {
-      const float4 p = __ldg(partial + ((size_t)b * S_stats + q) * G + g);
-      chan_merge(n, mean, m2, (double)p.x, (double)p.y, (double)p.z);
+      const double* p = partial + (((size_t)b * S_stats + q) * G + g) * 3;
+      chan_merge(n, mean, m2, p[0], p[1], p[2]);
     }
     g_mean[g] = (float)mean;
     g_rstd[g] = rsqrtf((float)(m2 / n) + eps);
@@ -202,14 +204,17 @@ apply_kernel(const __half* __restrict__ x, void* __restrict__ y, const float4* _
   for (; row < nrows; row += R) emit(__ldcs(xs + (size_t)row * C8 + col), row);
 }
 
-// row ranges per sample: enough CTAs to fill the GPU ~8 deep, at least 4 sweeps of rows per CTA
-static int pick_split(int B, int HW, int C) {
+// row ranges per sample: enough CTAs to fill the GPU ~8 deep; a range is a whole number of statistics blocks
+static void plan(int B, int HW, int C, int* S_out, int* rows_out) {
   const int R = NT / (C / 8);
+  const int BLK = BLK_SWEEPS * R;
+  const int nblk = ceil_div(HW, BLK);
   int S = ceil_div(148 * 8, B);
-  const int maxS = HW / (4 * R) > 0 ? HW / (4 * R) : 1;
-  if (S > maxS) S = maxS;
+  if (S > nblk) S = nblk;
   if (S < 1) S = 1;
-  return S;
+  const int rows = ceil_div(nblk, S) * BLK;
+  *S_out = ceil_div(HW, rows);
+  *rows_out = rows;
 }
 
 }  // namespace gnb
@@ -220,19 +225,22 @@ bool groupnorm_big_eligible(int B, int HW, int C, int G, int in_f16) {
 }
 
 size_t groupnorm_big_workspace(int B, int HW, int C, int G) {
-  return (size_t)B * gnb::pick_split(B, HW, C) * G * sizeof(float4);
+  int S, rows;
+  gnb::plan(B, HW, C, &S, &rows);
+  return (size_t)B * S * G * 3 * sizeof(double);
 }
 
 int groupnorm_big(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G, float eps,
                   int silu, int out_f16, void* workspace, size_t ws_bytes, cudaStream_t st) {
   using namespace gnb;
-  const int S = pick_split(B, HW, C);
-  CNB_REQUIRE(workspace && ws_bytes >= (size_t)B * S * G * sizeof(float4), "groupnorm: workspace too small");
-  const int rows = ceil_div(HW, S);
+  int S, rows;
+  plan(B, HW, C, &S, &rows);
+  CNB_REQUIRE(workspace && ws_bytes >= (size_t)B * S * G * 3 * sizeof(double), "groupnorm: workspace too small");
+  CNB_REQUIRE(G <= NT, "groupnorm_big: G=%d groups exceed %d", G, NT);
   const int R = NT / (C / 8);
   const size_t smem_stats = ((size_t)R * C * 2 + 2 * C) * sizeof(float);
   CNB_REQUIRE(smem_stats <= 48 * 1024, "groupnorm_big: smem %zu too large", smem_stats);
-  float4* partial = reinterpret_cast<float4*>(workspace);
+  double* partial = reinterpret_cast<double*>(workspace);
   stats_kernel<<<dim3(S, B), NT, smem_stats, st>>>(reinterpret_cast<const __half*>(x), partial, HW, C, G, rows);
   CNB_LAUNCH_CHECK();
   const size_t smem_apply = 2 * G * sizeof(float);

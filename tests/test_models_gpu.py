@@ -280,3 +280,50 @@ def test_teacher_predictions_vs_reference_golden(rt, tmp_path):
     ops = _mod("ops")
     got = ops.x0_from_eps(xc, eps.cuda(), sch.sqrt_one_minus_alpha_cum_prod.cuda(), sch.sqrt_alpha_cum_prod.cuda(), t.cuda())
     assert torch.equal(got.cpu(), want)
+
+
+def test_batch_invariance_at_baseline_sizes(rt):
+    """Size-independent property at BASELINE.json's full batch sizes: every sample is independent (GroupNorm and
+    attention are per sample, t is shared), so row b of a large-batch forward must equal the forward of sample b in a
+    small batch.  MNIST ControlNet at B = 1024 (config 2 shard), consistency student at B = 4096 (config 4), DM student
+    on CIFAR shapes at B = 2048 (config 5 sweep)."""
+    rt.set_mode("tf32" if rt.lib().cnb_has_tcgen05() else "fp32")
+    picks = [0, 1, 517, -1]
+
+    def check(fwd_big, fwd_small, n):
+        big = fwd_big()
+        assert torch.isfinite(big).all()
+        idx = [p % n for p in picks]
+        small = fwd_small(idx)
+        assert rel_l2(big[idx].cpu(), small.cpu()) < 1e-6
+
+    with torch.no_grad():
+        cfg = syn.MNIST_PARAMS
+        m = _fill(_mod("models.controlnet").ControlNet(cfg))
+        B = 1024
+        x = torch.randn(B, 1, 28, 28, device="cuda")
+        hint = (torch.rand(B, 1, 28, 28, device="cuda") < 0.1).float().expand(B, 3, 28, 28).contiguous()
+        t = torch.tensor([321], device="cuda")
+        check(lambda: m(x, t, hint), lambda i: m(x[i].contiguous(), t, hint[i].contiguous()), B)
+        del m
+        cs = _fill(_mod("models.consistency_controlnet_distilled").ConsistencyControlNet(cfg))
+        B = 4096
+        x = torch.randn(B, 1, 28, 28, device="cuda")
+        hint = (torch.rand(B, 1, 28, 28, device="cuda") < 0.1).float().expand(B, 3, 28, 28).contiguous()
+        sig = torch.full((B,), 80.0, device="cuda")
+        check(lambda: cs(x, sig, hint), lambda i: cs(x[i].contiguous(), sig[i].contiguous(), hint[i].contiguous()), B)
+        del cs
+        cfg = syn.CIFAR_PARAMS
+        dm = _fill(_mod("models.distribution_matching_controlnet").DistributionMatchingControlNet(cfg))
+        B = 2048
+        x = torch.randn(B, 3, 32, 32, device="cuda")
+        hint = (torch.rand(B, 1, 32, 32, device="cuda") < 0.1).float().expand(B, 3, 32, 32).contiguous()
+        tt = torch.full((B,), 999, device="cuda")
+        check(lambda: dm(x, tt, hint), lambda i: dm(x[i].contiguous(), tt[i].contiguous(), hint[i].contiguous()), B)
+        del dm
+        # VAE decoder: the split-statistics GroupNorm picks its number of row ranges from the batch size
+        vae = _fill(_mod("models.vae").VAE(3, syn.CELEBHQ_VAE_PARAMS))
+        z = torch.randn(40, 4, 32, 32, device="cuda")
+        big = vae.decode(z)
+        assert rel_l2(big[[0, 39]].cpu(), vae.decode(z[[0, 39]].contiguous()).cpu()) < 1e-6
+    assert rt.lib().cnb_tc_error_flag() == 0
