@@ -226,7 +226,20 @@ int conv2d_tma(const cnb_conv_params* p, cudaStream_t st) {
     a.kchunks2 = ceil_div(p->Cin2, kc);
   }
   // ---- packed weights [Cout][K] -> tile {kc, BN}
-  const int bn = pick_bn(p->Cout);
+  int bn = pick_bn(p->Cout);
+  if (!halo) {
+    // latency regime (small batch): fewer tiles than a quarter of the SMs means a handful of CTAs stream all the weights of the
+    // layer; narrower N tiles spread them over more SMs (the K order, hence the result, does not change)
+    const int tiles_m = ceil_div((long long)p->B * p->OH * p->OW, BM);
+    if (tiles_m * (p->Cout / bn) * 4 <= g_num_sms) {
+      static const int cand[] = {128, 96, 64, 48, 32};
+      for (int c : cand) {
+        if (c >= bn || p->Cout % c) continue;
+        bn = c;
+        if (tiles_m * (p->Cout / bn) * 2 >= g_num_sms) break;
+      }
+    }
+  }
   {
     const int K = p->ntaps * p->Cin + (p->in2 ? p->Cin2 : 0);
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)p->Cout};

@@ -71,8 +71,8 @@ class ConsistencyControlNet(nn.Module):
         flag = torch.empty((1,), device=dev, dtype=torch.int32)
         rt.check(rt.lib().cnb_edm_coeffs(sig.data_ptr(), B, float(self.sigma_data), float(self.sigma_min),
                                          coef.data_ptr(), t_index.data_ptr(), flag.data_ptr(), rt.stream()))
-        if int(flag.item()):          # host sync, exactly like the reference's `if torch.all(...)`
-            return x_t
+        if not getattr(self, "_skip_boundary_sync", False) and int(flag.item()):
+            return x_t                # host sync, exactly like the reference's `if torch.all(...)` (:81-82)
         mode = rt.get_mode()
         x_scaled = ops.scale_rows(coef[0], x_t)                       # c_in * x_t
         f_theta = student_body(self, ops.nchw_to_nhwc(x_scaled), t_index, hint, mode)

@@ -61,4 +61,10 @@ with torch.no_grad():
         x, h, t = torch.randn(B, 3, 32, 32, device="cuda"), hints(B, 32), torch.full((B,), 999, device="cuda")
         ms = timeit(lambda: m(x, t, h), reps=5 if B <= 1024 else 2)
         print(f"DM CIFAR           B={B:5d}: {ms:8.2f} ms  {B / ms * 1e3:10.0f} samples/s  {9.394 * B / ms:7.1f} TFLOP/s model", flush=True)
+    S = importlib.import_module("controlnet-pytorch_b200.sampler")
+    g = S.GraphedStudent(m)
+    for B in (1, 2, 4, 8, 16, 32, 64, 128, 256):
+        x, h, t = torch.randn(B, 3, 32, 32, device="cuda"), hints(B, 32), torch.full((B,), 999, device="cuda")
+        ms = timeit(lambda: g(x, t, h), reps=10)
+        print(f"DM CIFAR (graph)   B={B:5d}: {ms:8.3f} ms  {B / ms * 1e3:10.0f} samples/s  {9.394 * B / ms:7.1f} TFLOP/s model", flush=True)
 print("flag", rt.lib().cnb_tc_error_flag(), "mem GiB", torch.cuda.max_memory_allocated() / 2**30)

@@ -327,3 +327,25 @@ def test_batch_invariance_at_baseline_sizes(rt):
         big = vae.decode(z)
         assert rel_l2(big[[0, 39]].cpu(), vae.decode(z[[0, 39]].contiguous()).cpu()) < 1e-6
     assert rt.lib().cnb_tc_error_flag() == 0
+
+
+def test_graphed_students_match_eager(rt):
+    """sampler.GraphedStudent: one CUDA graph per input shape, new inputs copied into the static buffers; must equal
+    the eager forward bit for bit, also after the inputs change (hint block inside the graph) and at the boundary."""
+    rt.set_mode("tf32" if rt.lib().cnb_has_tcgen05() else "fp32")
+    S = _mod("sampler")
+    cfg = syn.TINY_PARAMS
+    dm = _fill(_mod("models.distribution_matching_controlnet").DistributionMatchingControlNet(cfg))
+    cs = _fill(_mod("models.consistency_controlnet_distilled").ConsistencyControlNet(cfg))
+    gdm, gcs = S.GraphedStudent(dm), S.GraphedStudent(cs)
+    with torch.no_grad():
+        for seed in (1, 2, 3):
+            x, hint = inputs(f"graphed{seed}", 3, cfg["im_channels"], cfg["im_size"])
+            xc, hc = x.cuda(), hint.cuda()
+            t = torch.tensor([999, 5, 300 + seed]).cuda()
+            assert torch.equal(gdm(xc, t, hc), dm(xc, t, hc))
+            sig = torch.tensor([80.0, 1.7, 0.01 * seed]).cuda()
+            assert torch.equal(gcs(xc, sig, hc), cs(xc, sig, hc))
+        small = torch.full((3,), 1e-3).cuda()
+        assert gcs(xc, small, hc) is xc                      # whole-batch early return, like the eager module
+    assert rt.lib().cnb_tc_error_flag() == 0
