@@ -241,6 +241,19 @@ int conv2d_tma(const cnb_conv_params* p, cudaStream_t st) {
     }
   }
   {
+    // experiment (CNB_CONV_2CTA=3): N tiles of at most 128 columns everywhere, so that every layer can run two CTAs per SM
+    static int two_env = -2;
+    if (two_env == -2) {
+      const char* e = getenv("CNB_CONV_2CTA");
+      two_env = e ? atoi(e) : 2;
+    }
+    if (two_env >= 3 && !halo && bn > 128) {
+      static const int cand[] = {128, 96, 64};
+      for (int c : cand)
+        if (p->Cout % c == 0) { bn = c; break; }
+    }
+  }
+  {
     const int K = p->ntaps * p->Cin + (p->in2 ? p->Cin2 : 0);
     const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)p->Cout};
     const cuuint64_t strides[1] = {(cuuint64_t)K * elt};

@@ -517,38 +517,66 @@ static int launch_epi(const TmaArgs& a_in, int num_sms, cudaStream_t st) {
   }
   TmaArgs a = a_in;
   const int ntiles = a.tiles_m * a.tiles_n;
-  const int grid = ntiles < num_sms ? ntiles : num_sms;
   const int nkb = a.ntaps * a.kchunks + a.kchunks2;
   const int b_res_bytes = (nkb * C::B_STAGE_BYTES + 1023) / 1024 * 1024;   // ring starts on a 1 KB boundary
-  const int room = SMEM_BUDGET - 1024 - C::EPI_BYTES - C::BAR_BYTES - b_res_bytes;
-  int s_res = room > 0 ? room / C::A_STAGE_BYTES : 0;
-  if (s_res > C::S) s_res = C::S;
-  size_t smem_bytes;
-  if (a.halo) {
-    int s_h = room > 0 ? room / a.halo_stage_bytes : 0;
-    if (s_h > C::S) s_h = C::S;
-    if (s_h < 2) {
-      set_error("conv_tma: halo plan does not fit shared memory (host-side check out of sync)");
+  // smem plan for a given per-CTA budget; returns the ring depth (0: does not fit)
+  auto plan = [&](int budget, int ctas, TmaArgs& o) -> int {
+    const int room = budget - 1024 - C::EPI_BYTES - C::BAR_BYTES - b_res_bytes;
+    int s_res = room > 0 ? room / C::A_STAGE_BYTES : 0;
+    if (s_res > C::S) s_res = C::S;
+    if (o.halo) {
+      int s_h = room > 0 ? room / o.halo_stage_bytes : 0;
+      if (s_h > C::S) s_h = C::S;
+      o.bres = 1;
+      o.s_run = s_h;
+      o.ring_off = b_res_bytes;
+      o.stage_bytes = o.halo_stage_bytes;
+      o.epi_off = o.ring_off + s_h * o.halo_stage_bytes;
+      return s_h;
+    }
+    if (g_bres_enabled() && o.tiles_n == 1 && ntiles >= 3 * ctas && s_res >= 4) {
+      o.bres = 1;
+      o.s_run = s_res;
+      o.ring_off = b_res_bytes;
+      o.stage_bytes = C::A_STAGE_BYTES;
+      o.epi_off = o.ring_off + s_res * C::A_STAGE_BYTES;
+      return s_res;
+    }
+    int s_ring = (budget - 1024 - C::EPI_BYTES - C::BAR_BYTES) / C::STAGE_BYTES;
+    if (s_ring > C::S) s_ring = C::S;
+    o.bres = 0;
+    o.s_run = s_ring;
+    o.ring_off = 0;
+    o.stage_bytes = C::STAGE_BYTES;
+    o.epi_off = s_ring * C::STAGE_BYTES;
+    return s_ring;
+  };
+  // Two CTAs per SM (half the shared memory each, TMEM 2 x <= 256 columns): two independent load -> MMA -> epilogue
+  // pipelines share an SM, which hides the per-tile latency chains of the short-K layers and lets the next kernel's
+  // prologue overlap this kernel's tail.  Needs BN <= 128 (TMEM) and a specialised epilogue (<= 102 registers).
+  static int two_env = -2;
+  if (two_env == -2) {
+    const char* e = getenv("CNB_CONV_2CTA");
+    two_env = e ? atoi(e) : 2;
+  }
+  int grid = ntiles < num_sms ? ntiles : num_sms;
+  bool two = false;
+  if (two_env && BN <= 128 && EPI != 3 && ntiles >= 2 * num_sms) {
+    TmaArgs t = a_in;
+    if (plan(112 * 1024, 2 * num_sms, t) >= (two_env >= 2 ? 2 : 3)) {
+      a = t;
+      two = true;
+      grid = ntiles < 2 * num_sms ? ntiles : 2 * num_sms;
+    }
+  }
+  if (!two) {
+    const int depth = plan(SMEM_BUDGET, grid, a);
+    if (depth < 2) {
+      set_error("conv_tma: smem plan does not fit shared memory (host-side check out of sync)");
       return CNB_ERR_UNSUPPORTED;
     }
-    a.bres = 1;
-    a.s_run = s_h;
-    a.ring_off = b_res_bytes;
-    a.stage_bytes = a.halo_stage_bytes;
-    a.epi_off = a.ring_off + s_h * a.halo_stage_bytes;
-  } else if (g_bres_enabled() && a.tiles_n == 1 && ntiles >= 3 * grid && s_res >= 4) {
-    a.bres = 1;
-    a.s_run = s_res;
-    a.ring_off = b_res_bytes;
-    a.stage_bytes = C::A_STAGE_BYTES;
-    a.epi_off = a.ring_off + s_res * C::A_STAGE_BYTES;
-  } else {
-    a.bres = 0;
-    a.s_run = C::S;
-    a.ring_off = 0;
-    a.stage_bytes = C::STAGE_BYTES;
-    a.epi_off = C::EPI_OFFSET;
   }
+  size_t smem_bytes;
   a.bar_off = a.epi_off + C::EPI_BYTES;
   {
     // alternate-tile epilogue when a tile's tensor work (~BN * K / 32 cycles) is shorter than its epilogue

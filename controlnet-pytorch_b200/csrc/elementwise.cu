@@ -83,12 +83,27 @@ __device__ __forceinline__ float philox_pick(float4 v, int k) {
   return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w));
 }
 
+// One Philox4x32-10 block yields the four normals of global elements 4q .. 4q+3; a thread owns one such block and
+// stores it with one float4 when the output is 16-byte aligned with the global element grid (same element -> value
+// mapping as the fused draw inside sched_step_kernel).
 __global__ void philox_normal_kernel(float* __restrict__ out, long long n, uint64_t seed, uint64_t step,
                                      uint64_t elem_offset) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint64_t g = elem_offset + (uint64_t)i;
-  out[i] = philox_pick(philox_normal4(seed, step, g >> 2), (int)(g & 3));
+  const uint64_t g0 = elem_offset & ~3ull;                       // first Philox block that overlaps the output
+  const long long nblk = (long long)(((elem_offset + (uint64_t)n + 3ull) >> 2) - (g0 >> 2));
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const bool vec = (elem_offset & 3ull) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nblk; q += stride) {
+    const float4 v = philox_normal4(seed, step, (g0 >> 2) + (uint64_t)q);
+    const long long i0 = (long long)(g0 + 4ull * (uint64_t)q) - (long long)elem_offset;   // output index of lane 0
+    if (vec && i0 + 4 <= n) {
+      reinterpret_cast<float4*>(out)[i0 >> 2] = v;
+    } else {
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (i0 + k >= 0 && i0 + k < n) out[i0 + k] = e[k];
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -355,7 +370,11 @@ extern "C" int cnb_sched_step(const float* xt, const float* eps, const float* z,
 extern "C" int cnb_philox_normal(float* out, long long n, uint64_t seed, uint64_t step, uint64_t elem_offset,
                                  cnb_stream_t s) {
   CNB_REQUIRE(n > 0 && out, "philox_normal: bad args");
-  philox_normal_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)s>>>(out, n, seed, step, elem_offset);
+  {
+    long long blocks = (n / 4 + 256) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    philox_normal_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(out, n, seed, step, elem_offset);
+  }
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }

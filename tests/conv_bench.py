@@ -93,4 +93,18 @@ if what in ("gn", "all"):
             by = ((2.0 if in16 else 4.0) + (2.0 if f16 else 4.0)) * x.numel()
             print(f"gn C={C} @{hw} in={'f16' if in16 else 'f32'} out={'f16' if f16 else 'f32'}: {ms * 1e3:8.1f} us  "
                   f"{by / ms / 1e6:8.1f} GB/s", flush=True)
+if what in ("elt", "all"):
+    # scheduler update / Philox noise at sizes where HBM bandwidth shows (in situ the 3 MB tensors of a step do not)
+    coef = torch.tensor([0.9, 0.43, 0.01, 0.995, 0.09, 1.0], device="cuda")
+    for n_mi in (1, 16, 64, 192):
+        n = n_mi << 20
+        xt, eps, z = (torch.randn(n, device="cuda") for _ in range(3))
+        prev, x0 = torch.empty_like(xt), torch.empty_like(xt)
+        for name, kw, by in (("z given, x0 out", dict(z=z, x0_out=x0), 20), ("philox, x0 out", dict(x0_out=x0), 16),
+                             ("philox, no x0", dict(want_x0=False), 12)):
+            ms = timeit(lambda: ops.sched_step(xt, eps, coef, out=prev, seed=3, step=7, **kw))
+            print(f"sched_step n={n_mi}Mi [{name}]: {ms * 1e3:8.1f} us  {by * n / ms / 1e6:8.1f} GB/s", flush=True)
+        ms = timeit(lambda: ops.philox_normal((n,), "cuda", 3, 9))
+        print(f"philox_normal n={n_mi}Mi: {ms * 1e3:8.1f} us  {4 * n / ms / 1e6:8.1f} GB/s (write only)", flush=True)
+        del xt, eps, z, prev, x0
 print("flag", rt.lib().cnb_tc_error_flag())
