@@ -114,7 +114,7 @@ struct Cfg {
 // 4 = dense fp16 out + fp16 residual (the fp16 activation stream), 5 = halo tiles with fp16 out (+ fp16 residual),
 // 3 = generic.
 template <int BN, bool HALF, int EPI, int RB>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, (BN <= 128 && EPI != 3) ? 2 : 1)   // two CTAs per SM: <= 102 registers
 conv_tma_kernel(const __grid_constant__ TmaArgs a) {
   using C = Cfg<BN, RB>;
   constexpr int S = C::S;
@@ -366,6 +366,35 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
           pix = ((long long)b * a.OHf + (oy * a.oy_mul + a.oy_add)) * a.OWf + (ox * a.ox_mul + a.ox_add);
         }
       }
+      // Halo tiles: the residual rows of this warp's first slab are fetched BEFORE the accumulator is waited for, so
+      // their ~1 us global latency overlaps the tile's MMAs instead of being exposed once per tile (3x3 64->64 @28 +
+      // residual: 220 -> 141 us).
+      float4 rv[32 / RPI];
+      auto load_residual = [&](int si) {
+        const int n = n0 + si * SLAB + sub_c;
+        if (EPI == 5) {
+          const __half* resh = reinterpret_cast<const __half*>(a.residual);
+          if (resh) {
+#pragma unroll
+            for (int i = 0; i < 32 / RPI; ++i) {
+              const int rp = __shfl_sync(0xffffffffu, pixi, i * RPI + sub_r);
+              rv[i] = rp >= 0 ? ld_half4(resh + (size_t)rp * ldr + a.res_coff + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        } else if (EPI == 1 || EPI == 4) {
+          const int rows_left = M - m_w - sub_r;
+#pragma unroll
+          for (int i = 0; i < 32 / RPI; ++i) {
+            if (i * RPI < rows_left) {
+              const size_t off = (size_t)(m_w + sub_r + i * RPI) * ldr + a.res_coff + n;
+              rv[i] = EPI == 1 ? __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.residual) + off))
+                               : ld_half4(reinterpret_cast<const __half*>(a.residual) + off);
+            }
+          }
+        }
+      };
+      const int si_first = alt ? 0 : par;
+      if (EPI == 5 && si_first < NSLAB) load_residual(si_first);
       const int acc = tcount & 1;
       if (!mbar_wait(&tfull_bar[acc], (uint32_t)((tcount >> 1) & 1), abort_flag)) break;
       tc_fence_after();
@@ -380,6 +409,7 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
         uint32_t r[SLAB];
 #pragma unroll
         for (int j = 0; j < SLAB / 16; ++j) tmem_ld16_nowait(t_addr + (uint32_t)(c0 + 16 * j), r + 16 * j);
+        if (EPI == 5 && si != si_first) load_residual(si);   // later slabs of halo tiles: overlaps tcgen05.ld + transpose
         tmem_ld_wait();
         if (si + sstep >= NSLAB) {        // this warp's last slab: hand its share of the TMEM buffer back
           tc_fence_before();
@@ -409,10 +439,7 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
             if (rp >= 0) {
               float4 o = *reinterpret_cast<const float4*>(slab + (size_t)(i * RPI + sub_r) * SSTR + sub_c);
               o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-              if (resh) {
-                const float4 t = ld_half4(resh + (size_t)rp * ldr + a.res_coff + n);
-                o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
-              }
+              if (resh) { o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w; }
               const __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
               *reinterpret_cast<uint2*>(outh + (size_t)rp * ldo + a.out_coff + n) =
                   make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
@@ -423,19 +450,9 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
           const int rows_left = M - m_w - sub_r;              // row rr + sub_r is valid iff rr < rows_left
           const float* sp = slab + (size_t)sub_r * SSTR + sub_c;
           const size_t o_off = (size_t)(m_w + sub_r) * ldo + a.out_coff + n;
-          float4 rv[32 / RPI];
-          if (EPI == 1) {
-            const float* rp = reinterpret_cast<const float*>(a.residual) + (size_t)(m_w + sub_r) * ldr + a.res_coff + n;
-#pragma unroll
-            for (int i = 0; i < 32 / RPI; ++i)
-              if (i * RPI < rows_left) rv[i] = __ldg(reinterpret_cast<const float4*>(rp + (size_t)i * RPI * ldr));
-          }
-          if (EPI == 4) {
-            const __half* rp = reinterpret_cast<const __half*>(a.residual) + (size_t)(m_w + sub_r) * ldr + a.res_coff + n;
-#pragma unroll
-            for (int i = 0; i < 32 / RPI; ++i)
-              if (i * RPI < rows_left) rv[i] = ld_half4(rp + (size_t)i * RPI * ldr);
-          }
+          // dense tiles fetch the residual here, right before it is consumed: issuing it before the accumulator wait or
+          // before tcgen05.wait::ld measured SLOWER on the BN = 256 layers (1x1 256->256 @7: 34 -> 39-42 us)
+          if (EPI == 1 || EPI == 4) load_residual(si);
 #pragma unroll
           for (int i = 0; i < 32 / RPI; ++i) {
             if (i * RPI < rows_left) {

@@ -61,7 +61,8 @@ if what in ("conv", "all"):
             bias = torch.randn(cout, device="cuda")
             oh = ops.out_size(kind, hw)
             out = torch.empty(B, oh, oh, cout, device="cuda", dtype=torch.float16 if (half and os.environ.get("CB_OUT16", "1") == "1") else torch.float32)
-            ms = timeit(lambda: ops.conv(x, w, kind, cout, bias=bias, out=out, mode=mode, weight_lp=wl,
+            res = torch.randn_like(out) if os.environ.get("CB_RES", "0") == "1" else None
+            ms = timeit(lambda: ops.conv(x, w, kind, cout, bias=bias, out=out, mode=mode, weight_lp=wl, residual=res,
                                       act=int(os.environ.get('CB_ACT', '0'))))
             fl = 2.0 * B * oh * oh * k * cin * cout
             by = x.numel() * x.element_size() + out.numel() * out.element_size() + w.numel() * (2 if half else 4)
