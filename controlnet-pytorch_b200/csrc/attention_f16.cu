@@ -329,7 +329,13 @@ template <int D, int BK>
 static int launch_l(const void* qkv, void* out, int B, int L, int E, int heads, cudaStream_t st) {
   if (L <= 16) return launch<D, 16, 1>(qkv, out, B, L, E, heads, st);
   if (L <= 32) return launch<D, 32, 2>(qkv, out, B, L, E, heads, st);
-  if (D > 64 || padded(L, 64, BK) < padded(L, 128, BK)) return launch<D, BK, 4>(qkv, out, B, L, E, heads, st);
+  static int tie4 = -1;                    // experiment: CNB_ATTN_NW4=1 prefers 4 warps when both paddings tie
+  if (tie4 < 0) {
+    const char* e = getenv("CNB_ATTN_NW4");
+    tie4 = e ? atoi(e) : 0;
+  }
+  if (D > 64 || padded(L, 64, BK) < padded(L, 128, BK) || (tie4 && padded(L, 64, BK) == padded(L, 128, BK)))
+    return launch<D, BK, 4>(qkv, out, B, L, E, heads, st);
   return launch<D, BK, 8>(qkv, out, B, L, E, heads, st);
 }
 
@@ -354,6 +360,9 @@ int attention_f16(const void* qkv, void* out, int B, int L, int E, int heads, cu
     if (d == 4) return af16::launch_l<4, 32>(qkv, out, B, L, E, heads, st);
     if (d == 16) return af16::launch_l<16, 32>(qkv, out, B, L, E, heads, st);
     if (d == 32) return af16::launch_l<32, 32>(qkv, out, B, L, E, heads, st);
+    if (d == 24) return af16::launch_l<24, 32>(qkv, out, B, L, E, heads, st);
+    if (d == 8) return af16::launch_l<8, 32>(qkv, out, B, L, E, heads, st);
+    if (d == 64) return af16::launch_l<64, 32>(qkv, out, B, L, E, heads, st);
   }
   if (bk_env == 16 && L > 64) {
     if (d == 4) return af16::launch_l<4, 16>(qkv, out, B, L, E, heads, st);

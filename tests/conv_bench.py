@@ -16,6 +16,7 @@ rt.lib()
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 B = int(os.environ.get("CB_BATCH", "1024"))
+B_LDM = int(os.environ.get("CB_BATCH_LDM", "256"))
 
 
 def timeit(fn):
@@ -71,18 +72,20 @@ if what in ("conv", "all"):
 
 if what in ("attn", "all"):
     for mode in ((rt.MODE_TF32, rt.MODE_F32) if os.environ.get("CB_FP32", "0") == "1" else (rt.MODE_TF32,)):
-        ashapes = [(784, 64, 4), (784, 16, 4), (196, 128, 4), (196, 32, 4), (49, 256, 4), (49, 128, 4), (49, 64, 4)]
+        ashapes = [(784, 64, 4), (784, 16, 4), (196, 128, 4), (196, 32, 4), (49, 256, 4), (49, 128, 4), (49, 64, 4),
+                   (1024, 384, 16), (1024, 128, 16), (256, 512, 16), (64, 768, 16)]   # last four: CelebHQ LDM levels
         if os.environ.get("CB_ONLY"):
             ashapes = [ashapes[int(i)] for i in os.environ["CB_ONLY"].split(",")]
         for L, E, heads in ashapes:
             side = int(math.isqrt(L))
-            qkv = torch.randn(B, side, side, 3 * E, device="cuda")
+            Bq = B_LDM if heads == 16 else B
+            qkv = torch.randn(Bq, side, side, 3 * E, device="cuda")
             if os.environ.get("CB_ATTN_F16", "1") == "1" and mode != rt.MODE_F32:
                 qkv = qkv.half()
             ms = timeit(lambda: ops.attention(qkv, heads, mode=mode, tc05=os.environ.get('CB_TC05', '0') == '1'))
-            fl = 4.0 * B * L * L * E
+            fl = 4.0 * Bq * L * L * E
             print(f"attn[{rt.mode_name(mode)}] L={L} E={E} d={E // heads}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:8.2f} TFLOP/s  "
-                  f"{B * heads * L * L / ms / 1e6:8.2f} Gscore/s", flush=True)
+                  f"{Bq * heads * L * L / ms / 1e6:8.2f} Gscore/s", flush=True)
 
 if what in ("gn", "all"):
     for C, hw, G in [(64, 28, 8), (32, 28, 8), (16, 28, 8), (128, 14, 8), (256, 7, 8), (128, 7, 8)]:
