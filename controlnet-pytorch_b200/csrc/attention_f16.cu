@@ -69,8 +69,18 @@ __device__ __forceinline__ uint32_t ex2_h2(uint32_t x) {
 //     scores; the argument fma(s, c, -m c) <= 0 is formed in fp32 and rounded to fp16 once).
 // The softmax denominator is accumulated by the tensor core as one more output column tile whose B fragment is the
 // constant half2(1, 1): l = P . 1 in fp32, consistent with the fp16 P that multiplies V.
+// Key tiles processed per block barrier.  The narrow heads at 4 warps per CTA spent 14 % of their cycles at the one
+// barrier per 64-key tile (ncu: stall_barrier), so they take two tiles per barrier from a six-slot ring.
+#ifndef ATTN_SUB2
+#define ATTN_SUB2 0
+#endif
+__host__ __device__ constexpr int attn_sub(int D, int BK, int NW) { return (ATTN_SUB2 && D <= 16 && BK == 64 && NW == 4) ? 2 : 1; }
+
+#ifndef ATTN_MIN_BLOCKS
+#define ATTN_MIN_BLOCKS 7
+#endif
 template <int D, int BK, int NW, bool H2>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NW * 32, (NW == 4 && D <= 16) ? ATTN_MIN_BLOCKS : 0)
 attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int L, int E, float scale_log2) {
   constexpr int d = D;
   constexpr int DP = (D + 15) / 16 * 16;         // K extent of Q K^T
@@ -81,8 +91,10 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
   constexpr int NT = BK / 8;                     // S column tiles
   constexpr int KS = DP / 16;                    // k-steps of Q K^T
   constexpr int THREADS = NW * 32;
+  constexpr int SUB = attn_sub(D, BK, NW);       // key tiles per block barrier
+  constexpr int NSLOT = 3 * SUB;                 // smem ring: three groups of SUB tiles
   static_assert(BK % 16 == 0, "BK must be a multiple of 16");
-  extern __shared__ __align__(16) __half smem[];   // [3 stages][K | V][BK][STRIDE]
+  extern __shared__ __align__(16) __half smem[];   // [3 * SUB slots][K | V][BK][STRIDE]
   pdl_trigger();
   pdl_wait();
 
@@ -97,7 +109,7 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
 
   // zero the pad columns once (cp.async only ever writes the d real columns)
   if (d < DP) {
-    for (int i = tid; i < 6 * TILE / 2; i += THREADS) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+    for (int i = tid; i < NSLOT * 2 * TILE / 2; i += THREADS) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
     __syncthreads();
   }
 
@@ -149,6 +161,13 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
         cp_async<CH>(dst + (uint32_t)TILE * 2u, kp + (size_t)E * 2, ok ? CH : 0u);
       }
     }
+  };
+  auto load_group = [&](int grp) {               // SUB consecutive tiles, one commit group
+#pragma unroll
+    for (int hh = 0; hh < SUB; ++hh) {
+      const int t = grp * SUB + hh;
+      if (t < ntiles) load_tile(t, t % NSLOT);
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
@@ -166,7 +185,7 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
     constexpr bool MASK = decltype(mask_tag)::value;
     constexpr int NG = decltype(ng_tag)::value;
     constexpr int NTA = NG * 2;                    // active S column tiles
-    const int stage = t % 3;
+    const int stage = t % NSLOT;
     const uint32_t sK = smem_u + (uint32_t)(stage * 2 * TILE) * 2u;
     const uint32_t sV = sK + (uint32_t)TILE * 2u;
 
@@ -250,26 +269,32 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
     }
   };
 
-  // 3-stage ring, ONE block barrier per tile: the barrier that publishes tile t also proves every warp has finished
-  // tile t-1, whose stage is exactly the one tile t+2 is loaded into right after it.
+  // Ring of three GROUPS of SUB tiles, ONE block barrier per group: the barrier that publishes group g also proves every
+  // warp has finished group g-1, whose slots are exactly the ones group g+2 is loaded into right after it.
   const bool active = q0 < L;
-  load_tile(0, 0);
-  if (ntiles > 1) load_tile(1, 1);
+  const int ngroups = (ntiles + SUB - 1) / SUB;
+  load_group(0);
+  if (ngroups > 1) load_group(1);
   const bool ragged = (L % BK) != 0;
-  for (int t = 0; t < ntiles; ++t) {
-    if (t + 1 < ntiles) asm volatile("cp.async.wait_group 1;" ::: "memory");
+  for (int grp = 0; grp < ngroups; ++grp) {
+    if (grp + 1 < ngroups) asm volatile("cp.async.wait_group 1;" ::: "memory");
     else asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    if (t + 2 < ntiles) load_tile(t + 2, (t + 2) % 3);
+    if (grp + 2 < ngroups) load_group(grp + 2);
     if (active) {                                  // warps whose 16 query rows are all padding only help with the loads
-      if (ragged && t == ntiles - 1) {
-        const int groups = (L - t * BK + 15) / 16;
-        if (groups == 1) tile_body(t, std::true_type{}, std::integral_constant<int, 1>{});
-        if constexpr (BK >= 32) { if (groups == 2) tile_body(t, std::true_type{}, std::integral_constant<int, 2>{}); }
-        if constexpr (BK >= 48) { if (groups == 3) tile_body(t, std::true_type{}, std::integral_constant<int, 3>{}); }
-        if constexpr (BK >= 64) { if (groups == 4) tile_body(t, std::true_type{}, std::integral_constant<int, 4>{}); }
-      } else {
-        tile_body(t, std::false_type{}, std::integral_constant<int, BK / 16>{});
+#pragma unroll
+      for (int hh = 0; hh < SUB; ++hh) {
+        const int t = grp * SUB + hh;
+        if (t >= ntiles) break;
+        if (ragged && t == ntiles - 1) {
+          const int groups = (L - t * BK + 15) / 16;
+          if (groups == 1) tile_body(t, std::true_type{}, std::integral_constant<int, 1>{});
+          if constexpr (BK >= 32) { if (groups == 2) tile_body(t, std::true_type{}, std::integral_constant<int, 2>{}); }
+          if constexpr (BK >= 48) { if (groups == 3) tile_body(t, std::true_type{}, std::integral_constant<int, 3>{}); }
+          if constexpr (BK >= 64) { if (groups == 4) tile_body(t, std::true_type{}, std::integral_constant<int, 4>{}); }
+        } else {
+          tile_body(t, std::false_type{}, std::integral_constant<int, BK / 16>{});
+        }
       }
     }
   }
@@ -293,7 +318,7 @@ static int g_h2 = -1;   // CNB_ATTN_EXP2H=1: ex2.approx.f16x2 exponentials (no f
 template <int D, int BK, int NW, bool H2>
 static int launch2(const void* qkv, void* out, int B, int L, int E, int heads, cudaStream_t st) {
   constexpr int DP = (D + 15) / 16 * 16;
-  constexpr size_t SMEM = (size_t)3 * 2 * BK * (DP + 8) * sizeof(__half);
+  constexpr size_t SMEM = (size_t)3 * attn_sub(D, BK, NW) * 2 * BK * (DP + 8) * sizeof(__half);
   static bool attr_set = false;
   if (!attr_set) {
     CNB_CUDA(cudaFuncSetAttribute(attention_f16_kernel<D, BK, NW, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize,

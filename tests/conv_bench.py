@@ -93,6 +93,8 @@ if what in ("gn", "all"):
         g, b = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
         for in16, f16 in ((False, False), (False, True), (True, True)):
             xi = x.half() if in16 else x
+            if os.environ.get('CB_GN16', '0') == '1' and not (in16 and f16):
+                continue
             ms = timeit(lambda: ops.groupnorm(xi, g, b, G, True, out_f16=f16))
             by = ((2.0 if in16 else 4.0) + (2.0 if f16 else 4.0)) * x.numel()
             print(f"gn C={C} @{hw} in={'f16' if in16 else 'f32'} out={'f16' if f16 else 'f32'}: {ms * 1e3:8.1f} us  "
