@@ -156,6 +156,29 @@ def test_groupnorm(pk, B, C, G, H, W, silu):
         assert rel_l2(nchw(got.float().cpu()), want_h) < tol
 
 
+@pytest.mark.parametrize("B,C,G,H,W", [(1, 128, 32, 128, 128), (3, 256, 32, 64, 64), (2, 384, 32, 64, 64), (5, 256, 8, 32, 32),
+                                       (2, 64, 8, 61, 67), (1, 384, 32, 33, 31), (70, 128, 32, 32, 32)])
+@pytest.mark.parametrize("silu", [False, True])
+def test_groupnorm_large_samples(pk, B, C, G, H, W, silu):
+    """Split-statistics GroupNorm (cnb_groupnorm_ws: samples beyond one CTA's shared memory, VAE decoder / CelebHQ
+    levels): fp16 in, fp16 and fp32 out, odd spatial sizes, 384 channels (5 rows per sweep), a mean far from zero
+    (the shifted sums must not cancel) and batch invariance of the statistics."""
+    ops, rt = pk
+    x = (rnd(B, C, H, W, seed=4) * 1.5 + 6.0).half()
+    g, b = 1 + 0.1 * rnd(C, seed=5), 0.1 * rnd(C, seed=6)
+    assert rt.lib().cnb_groupnorm_workspace_bytes(B, H * W, C, G, 1) > 0          # this shape takes the split kernels
+    want = F.group_norm(x.float(), G, g, b, eps=1e-5)
+    if silu:
+        want = F.silu(want)
+    xc = nhwc(x).cuda()
+    for o16, tol in ((True, 6e-4), (False, 4e-6)):
+        got = ops.groupnorm(xc, g.cuda(), b.cuda(), G, silu, out_f16=o16)
+        assert rel_l2(nchw(got.float().cpu()), want) < tol, (o16, rel_l2(nchw(got.float().cpu()), want))
+    if B > 1:   # the number of row ranges follows the batch size; the result must not
+        one = ops.groupnorm(xc[:1].contiguous(), g.cuda(), b.cuda(), G, silu, out_f16=True)
+        assert torch.equal(one, ops.groupnorm(xc, g.cuda(), b.cuda(), G, silu, out_f16=True)[:1])
+
+
 @pytest.mark.parametrize("B,L,E,heads", [(2, 784, 64, 4), (2, 784, 16, 4), (3, 196, 128, 4), (2, 49, 256, 4),
                                          (2, 196, 32, 4), (1, 1024, 384, 16), (2, 64, 768, 16), (2, 16, 512, 16),
                                          (1, 64, 512, 4), (1, 100, 384, 4), (1, 50, 768, 4), (2, 1, 64, 4), (1, 13, 32, 4)])
