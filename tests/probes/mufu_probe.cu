@@ -23,6 +23,21 @@ __device__ float run_kind(int kind, int iters, float seed) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[0]) : "f"(0.999f), "f"(0.001f));
     }
+  } else if (kind == 5) {          // ex2.approx.f16x2: two exponentials per instruction
+    unsigned h[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) h[i] = __float_as_uint(a[i]) & 0x3BFF3BFFu;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(h[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(h[i]);
+  } else if (kind == 6) {          // tanh.approx.f32
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a[i]));
+    }
   } else if (kind == 4) {
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -50,8 +65,8 @@ __global__ void probe(int kindA, int kindB, int iters, long long* out, float* si
 int main() {
   long long* d; float* sink; cudaMalloc(&d, 64); cudaMalloc(&sink, 4096);
   const int iters = 256;   // x16 instructions
-  const char* nm[5] = {"idle", "MUFU", "FFMA-indep", "FFMA-chain", "FFMA+MUFU"};
-  for (int ka : {0, 1, 4}) for (int kb : {0, 1, 2, 3, 4}) {
+  const char* nm[7] = {"idle", "MUFU", "FFMA-indep", "FFMA-chain", "FFMA+MUFU", "EX2.F16x2", "TANH"};
+  for (int ka : {0, 1, 5}) for (int kb : {0, 1, 5, 6}) {
     probe<<<1, 256>>>(ka, kb, iters, d, sink);
     cudaDeviceSynchronize();
     long long h[8]; cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
