@@ -222,13 +222,15 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
       mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
       mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    // Lazy reference maximum: it only moves when a tile maximum exceeds it by more than 2^LAZY (P <= 2^LAZY is harmless
-    // in fp16, the sums are fp32), so after the first tiles the correction (2 MUFU + the O / l rescale) is skipped.
+    // Lazy reference maximum: it only moves when a score exceeds it by more than 2^LAZY (P <= 2^LAZY is harmless in
+    // fp16, the sums are fp32).  The test is per lane on its own 2 x 2 NTA scores -- no quad shuffles on the common path;
+    // only when some lane of the warp trips it are the row maxima reduced across the quad and the correction
+    // (2 MUFU + the O / l rescale) applied, which after the first tiles is rare.
     if (__any_sync(0xffffffffu, mx0 > m0 + lazy || mx1 > m1 + lazy)) {
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
       const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // finite: every tile has >= 1 valid key
       const float cr0 = ex2((m0 - mn0) * scale_log2), cr1 = ex2((m1 - mn1) * scale_log2);
       m0 = mn0; m1 = mn1;
