@@ -153,7 +153,7 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
   // 64-bit add per slot and tile) instead of being recomputed from t -- the address arithmetic was ~15 % of a tile's
   // instructions; measured it pays only where registers are not tight (d = 16, 4 warps: 926 -> 903 us; the other
   // instantiations lose 1-6 % to the extra live registers and keep the recomputation).
-  constexpr bool RUN_PTR = (D == 16 && NW == 4);
+  constexpr bool RUN_PTR = (D <= 16 && NW == 4);
   const char* ld_src[SLOTS];
   uint32_t ld_dst[SLOTS];
   int ld_key[SLOTS];
