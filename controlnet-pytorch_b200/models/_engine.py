@@ -430,18 +430,24 @@ def hint_stack_ddpm(seq, hint_nhwc, mode):
 
 
 class HintCache:
-    """hint_block(hint) depends on neither t nor x (controlnet.py:179): compute once per (hint object, weights).
-    The cache holds a reference to the hint tensor, so its storage cannot be recycled under the cached key."""
+    """hint_block(hint) depends on neither t nor x (controlnet.py:179): compute once per (hint storage, weights).
+    A few entries are kept (the split sampler runs batch halves of one hint tensor on parallel streams); every entry
+    holds a reference to its hint tensor, so the storage cannot be recycled under the cached key."""
+    MAX_ENTRIES = 8
 
     def __init__(self):
-        self.ref, self.key, self.val = None, None, None
+        self.entries = {}
 
     def get(self, hint, params, mode, fn):
-        key = (hint._version, tuple(hint.shape), mode, tuple((p._version, p.data_ptr()) for p in params))
-        if hint is not self.ref or key != self.key:
-            self.val = fn()
-            self.ref, self.key = hint, key
-        return self.val
+        key = (hint.data_ptr(), hint._version, tuple(hint.shape), tuple(hint.stride()), mode,
+               tuple((p._version, p.data_ptr()) for p in params))
+        ent = self.entries.get(key)
+        if ent is None:
+            if len(self.entries) >= self.MAX_ENTRIES:
+                self.entries.pop(next(iter(self.entries)))
+            ent = (hint, fn())
+            self.entries[key] = ent
+        return ent[1]
 
     def clear(self):
-        self.ref, self.key, self.val = None, None, None
+        self.entries = {}

