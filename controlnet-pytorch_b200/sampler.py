@@ -64,7 +64,10 @@ class DDPMSampler:
         # tensor- / HBM-bound convolutions and GroupNorms of the other (measured at B = 1024: 13.08 -> 12.65 ms).
         B = self.xt.shape[0]
         per = self.xt[0].numel()
-        nsplit = int(os.environ.get("CNB_SAMPLER_SPLIT", "2" if B >= 512 else "1"))
+        # (it pays once a half still fills the GPU: B >= 512 for the MNIST / CIFAR widths, B >= 128 for the 190 M-parameter
+        # CelebHQ model -- measured: MNIST B = 256 4.15 -> 4.39 ms (worse), CelebHQ B = 256 31.2 -> 30.5 ms)
+        big_model = sum(p.numel() for p in self.model.parameters()) > 50_000_000
+        nsplit = int(os.environ.get("CNB_SAMPLER_SPLIT", "2" if B >= (128 if big_model else 512) else "1"))
         nsplit = max(1, min(nsplit, B))
         bounds = [shard_bounds(B, nsplit, k) for k in range(nsplit)]
         self._split_streams = [torch.cuda.Stream(device=dev) for _ in range(nsplit)] if nsplit > 1 else []
