@@ -401,7 +401,8 @@ def run_b200(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": dtype_name, "data": "synthetic",
                 "config": {"workload": "mnist_ddpm_controlnet_1000step", "batch_per_gpu": B, "global_batch": world * B,
                            "timesteps_per_sample": STEPS_PER_SAMPLE,
-                           "step": "one denoising timestep: ControlNet eps + fused sample_prev_timestep (CUDA graph replay)",
+                           "step": "one denoising timestep: ControlNet eps + fused sample_prev_timestep (CUDA graph replay; "
+                                   "the two batch halves run on parallel capture streams inside the graph)",
                            "parallelism": f"dp{world} (batch-sharded, no collective in the loop)",
                            "l2": "inputs larger than L2: ~%.1f GB of activations per step vs 126 MB L2" % (
                                B * 2.98e6 * 4 * 2 / 1e9),
