@@ -64,10 +64,12 @@ class DDPMSampler:
         # tensor- / HBM-bound convolutions and GroupNorms of the other (measured at B = 1024: 13.08 -> 12.65 ms).
         B = self.xt.shape[0]
         per = self.xt[0].numel()
-        # (it pays once a half still fills the GPU: B >= 512 for the MNIST / CIFAR widths, B >= 128 for the 190 M-parameter
-        # CelebHQ model -- measured: MNIST B = 256 4.15 -> 4.39 ms (worse), CelebHQ B = 256 31.2 -> 30.5 ms)
+        # Default: off for the MNIST / CIFAR widths, where the ControlNet forward's own two-stream fork of its encoders
+        # (models/_controlnet_common.py) gives the same overlap without halving the per-kernel batch (B = 1024: 12.59
+        # split vs 12.61 branches vs 12.70 ms both); on for the 190 M-parameter CelebHQ model from B = 128, where the
+        # split measured better (B = 256: 31.2 unsplit, 31.1 branches, 30.5 ms split).  Never both.
         big_model = sum(p.numel() for p in self.model.parameters()) > 50_000_000
-        nsplit = int(os.environ.get("CNB_SAMPLER_SPLIT", "2" if B >= (128 if big_model else 512) else "1"))
+        nsplit = int(os.environ.get("CNB_SAMPLER_SPLIT", "2" if (big_model and B >= 128) else "1"))
         nsplit = max(1, min(nsplit, B))
         bounds = [shard_bounds(B, nsplit, k) for k in range(nsplit)]
         self._split_streams = [torch.cuda.Stream(device=dev) for _ in range(nsplit)] if nsplit > 1 else []
@@ -93,18 +95,23 @@ class DDPMSampler:
                     cur.wait_stream(st)
             rt.check(L.cnb_bump_index(self.step_idx.data_ptr(), 1, rt.stream()))
 
-        # warm-up on a side stream: builds weight / hint caches and sets kernel attributes outside the capture
-        s = torch.cuda.Stream(device=dev)
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            one_step()
-        torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize(dev)
-        c0 = rt.launch_count()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            one_step()
-        self.launches_per_step = rt.launch_count() - c0
+        from .models import _controlnet_common as _cc
+        _cc.set_branch_parallel(False if nsplit > 1 else None)
+        try:
+            # warm-up on a side stream: builds weight / hint caches and sets kernel attributes outside the capture
+            s = torch.cuda.Stream(device=dev)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                one_step()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize(dev)
+            c0 = rt.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                one_step()
+            self.launches_per_step = rt.launch_count() - c0
+        finally:
+            _cc.set_branch_parallel(None)
         self._graph = g
         self._nsteps, self._pos = steps, 0
 
