@@ -8,8 +8,9 @@
 //                  block's first row (no cancellation: |mean - p| ~ sigma); per-channel (n, mean, M2) are merged per
 //                  group with Chan's parallel-variance formula, blocks are merged in double and written as three
 //                  doubles per (sample, range, group)
-//   apply kernel   grid (S, B): merges the S partials of its sample (Chan again, double accumulators), folds gamma /
-//                  beta into one FMA per element, applies SiLU (tanh form for fp16 outputs) and stores 16 bytes
+//   finalize       one thread per (sample, group) merges the sample's block partials in block order (Chan, double)
+//   apply kernel   grid (S, B): folds mean / rstd / gamma / beta into one FMA per element, applies SiLU (tanh form for
+//                  fp16 outputs) and stores 16 bytes
 //
 // Algorithmic bytes: 2 B read + 2 B written per element; the second read of a range follows its first within a few
 // hundred microseconds and is an L2 hit whenever B * slab stays under the 126 MB L2, else DRAM sees 2 reads + 1 write.
@@ -53,7 +54,7 @@ __device__ __forceinline__ void chan_merge(T& n, T& mean, T& m2, T nb, T mb, T m
 // Statistics are computed on FIXED blocks of BLK_SWEEPS * R rows (fp32, deterministic per block) and merged in double,
 // so the result does not depend on how many row ranges S a sample is split into (S follows the batch size): GroupNorm
 // stays batch / shard invariant like the one-CTA-per-sample kernels.
-constexpr int BLK_SWEEPS = 16;
+constexpr int BLK_SWEEPS = 32;
 
 __global__ void __launch_bounds__(NT)
 stats_kernel(const __half* __restrict__ x, double* __restrict__ partial, int HW, int C, int G, int rows_per_cta) {
@@ -68,7 +69,7 @@ stats_kernel(const __half* __restrict__ x, double* __restrict__ partial, int HW,
   const int cta_rows = max(0, min(rows_per_cta, HW - cta_row0));
   const int BLK = BLK_SWEEPS * R;              // rows_per_cta is a multiple of BLK (host)
   const int cg = C / G;
-  double gn = 0.0, gmean = 0.0, gm2 = 0.0;     // running merge of this CTA's blocks (threads g < G)
+  const int nblk_total = (HW + BLK - 1) / BLK;  // blocks per sample (global block index = row0 / BLK)
   for (int blk0 = 0; blk0 < cta_rows; blk0 += BLK) {
     const int row0 = cta_row0 + blk0;
     const int nrows = min(BLK, cta_rows - blk0);
@@ -113,7 +114,6 @@ stats_kernel(const __half* __restrict__ x, double* __restrict__ partial, int HW,
       }
     }
     __syncthreads();
-    // per channel: row class r covers rows r, r + R, ... of the block; each class has its own count
     for (int c = tid; c < C; c += NT) {
       const float p = __half2float(x[((size_t)b * HW + row0) * C + c]);
       float s1 = 0.f, s2 = 0.f;
@@ -126,24 +126,37 @@ stats_kernel(const __half* __restrict__ x, double* __restrict__ partial, int HW,
       cstat[2 * c + 1] = fmaxf(s2 - s1 * dm, 0.f);
     }
     __syncthreads();
+    // one (n, mean, M2) triple per (sample, BLOCK, group): the apply kernel merges a sample's blocks in block order, so
+    // the statistics are bit-identical however the blocks were distributed over CTAs
     for (int g = tid; g < G; g += NT) {
       float n = 0.f, mean = 0.f, m2 = 0.f;
       for (int c = 0; c < cg; ++c) chan_merge(n, mean, m2, (float)nrows, cstat[2 * (g * cg + c)], cstat[2 * (g * cg + c) + 1]);
-      chan_merge(gn, gmean, gm2, (double)n, (double)mean, (double)m2);
+      double* o = partial + (((size_t)b * nblk_total + row0 / BLK) * G + g) * 3;
+      o[0] = (double)n; o[1] = (double)mean; o[2] = (double)m2;
     }
     // (the next block's writes to part / cstat are ordered behind these reads by its own two barriers)
   }
-  for (int g = tid; g < G; g += NT) {          // G <= NT: each thread owns at most one group
-    double* o = partial + (((size_t)b * S + s) * G + g) * 3;
-    o[0] = gn; o[1] = gmean; o[2] = gm2;
+}
+
+// One thread per (sample, group): merge the sample's block partials in block order (double, Chan) -> mean, rstd.
+__global__ void finalize_kernel(const double* __restrict__ partial, float2* __restrict__ stats, int BG, int G,
+                                int nblk_total, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BG) return;
+  const int b = i / G, g = i - b * G;
+  double n = 0.0, mean = 0.0, m2 = 0.0;
+  for (int q = 0; q < nblk_total; ++q) {                 // fixed block order: independent of the CTA split
+    const double* p = partial + (((size_t)b * nblk_total + q) * G + g) * 3;
+    chan_merge(n, mean, m2, p[0], p[1], p[2]);
   }
+  stats[i] = make_float2((float)mean, rsqrtf((float)(m2 / n) + eps));
 }
 
 template <bool SILU, bool HALF>
 __global__ void __launch_bounds__(NT)
-apply_kernel(const __half* __restrict__ x, void* __restrict__ y, const double* __restrict__ partial,
+apply_kernel(const __half* __restrict__ x, void* __restrict__ y, const float2* __restrict__ stats,
              const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C, int G, float eps,
-             int rows_per_cta, int S_stats) {
+             int rows_per_cta) {
   extern __shared__ float sm[];
   float* g_mean = sm;            // [G]
   float* g_rstd = sm + G;        // [G]
@@ -152,13 +165,9 @@ apply_kernel(const __half* __restrict__ x, void* __restrict__ y, const double* _
   const int tid = threadIdx.x, col = tid % C8, r0 = tid / C8;
   const int s = blockIdx.x, b = blockIdx.y;
   for (int g = tid; g < G; g += NT) {
-    double n = 0.0, mean = 0.0, m2 = 0.0;
-    for (int q = 0; q < S_stats; ++q) {
-      const double* p = partial + (((size_t)b * S_stats + q) * G + g) * 3;
-      chan_merge(n, mean, m2, p[0], p[1], p[2]);
-    }
-    g_mean[g] = (float)mean;
-    g_rstd[g] = rsqrtf((float)(m2 / n) + eps);
+    const float2 st = __ldg(stats + (size_t)b * G + g);
+    g_mean[g] = st.x;
+    g_rstd[g] = st.y;
   }
   __syncthreads();
   if (r0 >= R) return;
@@ -233,7 +242,10 @@ bool groupnorm_big_eligible(int B, int HW, int C, int G, int in_f16) {
 size_t groupnorm_big_workspace(int B, int HW, int C, int G) {
   int S, rows;
   gnb::plan(B, HW, C, &S, &rows);
-  return (size_t)B * S * G * 3 * sizeof(double);
+  (void)S;
+  const int R = gnb::NT / (C / 8);
+  const int nblk = ceil_div(HW, gnb::BLK_SWEEPS * R);
+  return (size_t)B * nblk * G * 3 * sizeof(double) + (size_t)B * G * sizeof(float2);
 }
 
 int groupnorm_big(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G, float eps,
@@ -241,23 +253,27 @@ int groupnorm_big(const void* x, void* y, const float* gamma, const float* beta,
   using namespace gnb;
   int S, rows;
   plan(B, HW, C, &S, &rows);
-  CNB_REQUIRE(workspace && ws_bytes >= (size_t)B * S * G * 3 * sizeof(double), "groupnorm: workspace too small");
-  CNB_REQUIRE(G <= NT, "groupnorm_big: G=%d groups exceed %d", G, NT);
   const int R = NT / (C / 8);
+  const int nblk = ceil_div(HW, BLK_SWEEPS * R);
+  const size_t partial_bytes = (size_t)B * nblk * G * 3 * sizeof(double);
+  CNB_REQUIRE(workspace && ws_bytes >= partial_bytes + (size_t)B * G * sizeof(float2), "groupnorm: workspace too small");
   const size_t smem_stats = ((size_t)R * C * 2 + 2 * C) * sizeof(float);
   CNB_REQUIRE(smem_stats <= 48 * 1024, "groupnorm_big: smem %zu too large", smem_stats);
   double* partial = reinterpret_cast<double*>(workspace);
   stats_kernel<<<dim3(S, B), NT, smem_stats, st>>>(reinterpret_cast<const __half*>(x), partial, HW, C, G, rows);
   CNB_LAUNCH_CHECK();
+  float2* stats = reinterpret_cast<float2*>(reinterpret_cast<char*>(workspace) + partial_bytes);
+  finalize_kernel<<<ceil_div(B * G, 128), 128, 0, st>>>(partial, stats, B * G, G, nblk, eps);
+  CNB_LAUNCH_CHECK();
   const size_t smem_apply = 2 * G * sizeof(float);
   const __half* xh = reinterpret_cast<const __half*>(x);
   const dim3 grid(S, B);
   if (silu) {
-    if (out_f16) apply_kernel<true, true><<<grid, NT, smem_apply, st>>>(xh, y, partial, gamma, beta, HW, C, G, eps, rows, S);
-    else apply_kernel<true, false><<<grid, NT, smem_apply, st>>>(xh, y, partial, gamma, beta, HW, C, G, eps, rows, S);
+    if (out_f16) apply_kernel<true, true><<<grid, NT, smem_apply, st>>>(xh, y, stats, gamma, beta, HW, C, G, eps, rows);
+    else apply_kernel<true, false><<<grid, NT, smem_apply, st>>>(xh, y, stats, gamma, beta, HW, C, G, eps, rows);
   } else {
-    if (out_f16) apply_kernel<false, true><<<grid, NT, smem_apply, st>>>(xh, y, partial, gamma, beta, HW, C, G, eps, rows, S);
-    else apply_kernel<false, false><<<grid, NT, smem_apply, st>>>(xh, y, partial, gamma, beta, HW, C, G, eps, rows, S);
+    if (out_f16) apply_kernel<false, true><<<grid, NT, smem_apply, st>>>(xh, y, stats, gamma, beta, HW, C, G, eps, rows);
+    else apply_kernel<false, false><<<grid, NT, smem_apply, st>>>(xh, y, stats, gamma, beta, HW, C, G, eps, rows);
   }
   CNB_LAUNCH_CHECK();
   return CNB_OK;

@@ -64,7 +64,7 @@ class VAE(nn.Module):
 
     def _decode_nhwc(self, z_nhwc, mode):
         h = self._conv(self.post_quant_conv, z_nhwc, "1x1", mode)
-        h = self._conv(self.decoder_conv_in, h, "3x3", mode)
+        h = E.conv3x3_narrow_in(self.decoder_conv_in, h, mode)
         for mid in self.decoder_mids:
             h = E.run_mid(mid, h, None, mode)
         for up in self.decoder_layers:
@@ -76,7 +76,7 @@ class VAE(nn.Module):
         return ops.nhwc_to_nchw(self._decode_nhwc(ops.nchw_to_nhwc(E._check_x(z)), mode))
 
     def _encode_out(self, x, mode):
-        h = self._conv(self.encoder_conv_in, ops.nchw_to_nhwc(E._check_x(x)), "3x3", mode)
+        h = E.conv3x3_narrow_in(self.encoder_conv_in, ops.nchw_to_nhwc(E._check_x(x)), mode)
         for down in self.encoder_layers:
             h = E.run_down(down, h, None, mode)
         for mid in self.encoder_mids:
