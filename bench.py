@@ -223,6 +223,26 @@ def make_roofline(fams, step_ms, batch):
                      "pipe: see `xu` and DESIGN.md 4.2")
         r["xu"] = {"achieved": round(ts, 3), "peak": round(MUFU_PEAK_TSCORES, 3), "unit": "Tscore/s",
                    "frac": round(ts / MUFU_PEAK_TSCORES, 3)}
+    # the other families against their own rooflines (BASELINE metric: conv tensor-pipe % of peak, fused norm kernels
+    # as a fraction of HBM bandwidth): dominant layer shape of the family and its best layer shape
+    def shape_line(fam_, shape_, sh_):
+        sec_ = sh_["ms"] * 1e-3 / sh_["launches"]
+        if fam_ == "conv_tc":
+            a_ = sh_["flops"] / sh_["launches"] / sec_ / 1e12
+            return {"shape": shape_, "bound": "tensor", "achieved": round(a_, 1), "peak": pk["tf"], "unit": "TFLOP/s",
+                    "frac": round(a_ / pk["tf"], 3), "avg_launch_us": round(sec_ * 1e6, 1),
+                    "traffic": NCU_TRAFFIC.get((fam_, shape_, batch))}
+        a_ = sh_["bytes"] / sh_["launches"] / sec_ / 1e9
+        return {"shape": shape_, "bound": "hbm", "achieved": round(a_, 1), "peak": pk["hbm"], "unit": "GB/s",
+                "frac": round(a_ / pk["hbm"], 3), "avg_launch_us": round(sec_ * 1e6, 1)}
+    by_family = {}
+    for fam_ in ("conv_tc", "groupnorm"):
+        if fam_ not in fams:
+            continue
+        lines = [shape_line(fam_, s_, v_) for s_, v_ in sorted(fams[fam_]["shapes"].items(), key=lambda kv: -kv[1]["ms"])]
+        by_family[fam_] = {"dominant": lines[0], "best": max(lines, key=lambda l_: l_["frac"]),
+                           "family_share_of_step": round(fams[fam_]["ms"] / total, 3)}
+    r["by_family"] = by_family
     fam_out = {}
     for k_, v in fams.items():
         s_ = v["ms"] * 1e-3
