@@ -72,6 +72,20 @@ def trajectory(model, sched, x, hint, steps, name):
 
 
 @torch.no_grad()
+def make_config1():
+    """BASELINE.json configs[0]: MNIST DDPM ControlNet, batch 16, 50 steps (t = 49 .. 0, the semantics of
+    tools/compare_all_controlnet_models.py) with the per-step z injected; the final x_0 / x_{t-1} of
+    the unmodified reference are the fixture the PSNR / max-abs bound of the parity tests is stated against."""
+    cfg = syn.MNIST_PARAMS
+    m = fill(RefControlNet(cfg))
+    x, hint = inputs("config1", 16, cfg["im_channels"], cfg["im_size"])
+    sched = RefSched(**syn.MNIST_DIFFUSION)
+    xt, x0 = trajectory(m, sched, x, hint, 50, "config1")
+    np.savez_compressed(os.path.join(OUT, "config1_mnist_b16_50step.npz"), xt=xt.numpy(), x0=x0.numpy())
+    print("config1", tuple(xt.shape), float(x0.abs().max()), float(x0.std()))
+
+
+@torch.no_grad()
 def make_teachers():
     """Teacher-side inference of the distillation wrappers: get_teacher_prediction with per-sample t
     and get_ddpm_teacher_prediction / sigma_to_timestep; the teacher checkpoint is a det_state_dict ControlNet."""
@@ -136,6 +150,8 @@ def main():
         return make_vae()
     if "--only-teachers" in sys.argv:
         return make_teachers()
+    if "--only-config1" in sys.argv:
+        return make_config1()
 
     # ---- DDPM ControlNet: tiny / mnist / cifar
     for name, cfg, B, ts in (("tiny", syn.TINY_PARAMS, 2, (999, 37, 0)),
@@ -227,6 +243,7 @@ def main():
         json.dump(man, f)
     make_vae()
     make_teachers()
+    make_config1()
     print("done ->", OUT)
 
 

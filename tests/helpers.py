@@ -19,6 +19,18 @@ def rel_l2(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
+def psnr(a, b, peak_to_peak=2.0):
+    """PSNR in dB of images in [-1, 1] (peak-to-peak 2, as written by the sampling tools before the [0, 1] map)."""
+    a = torch.as_tensor(a).double().flatten()
+    b = torch.as_tensor(b).double().flatten()
+    mse = float(((a - b) ** 2).mean())
+    return float("inf") if mse == 0.0 else 10.0 * float(np.log10(peak_to_peak ** 2 / mse))
+
+
+def max_abs(a, b):
+    return float((torch.as_tensor(a).double() - torch.as_tensor(b).double()).abs().max())
+
+
 def golden(name):
     return np.load(os.path.join(GOLDEN, name + ".npz"))
 

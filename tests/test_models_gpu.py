@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import golden, inputs, rel_l2, syn, ROOT
+from helpers import golden, inputs, max_abs, psnr, rel_l2, syn, ROOT
 
 pytestmark = pytest.mark.gpu
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -67,6 +67,30 @@ def test_controlnet_ddpm_vs_reference_golden(rt, name, cfg, B, ts):
                 xt, x0 = smp.sample_eager(xc, hc, steps=3, zs=zs)
                 assert rel_l2(xt.cpu(), g["traj3_xt"]) < TRAJ_TOL[mode]
                 assert rel_l2(x0.cpu(), g["traj3_x0"]) < TRAJ_TOL[mode]
+    assert rt.lib().cnb_tc_error_flag() == 0
+
+
+# BASELINE.json: "the final x0 matches within a stated PSNR / max-abs bound".  Stated here for configs[0] (MNIST
+# ControlNet, batch 16, 50 steps, images in [-1, 1]); measured on a B200 (tests/config1_check.py,
+# profiles/r01_config1_check.log): fp32 mode 147 dB / 8.3e-7, tensor-core mode 83 dB / 6.7e-4.
+X0_BOUND = {"fp32": dict(psnr_db=120.0, max_abs=1e-5), "tf32": dict(psnr_db=65.0, max_abs=5e-3)}
+
+
+def test_config1_mnist_b16_50step_final_x0_vs_reference_golden(rt):
+    """BASELINE.json configs[0]: 50 denoising steps (t = 49 .. 0) at batch 16 with the per-step z injected, against
+    the final x_0 / x_{t-1} of the unmodified reference (tests/golden/config1_mnist_b16_50step.npz)."""
+    cfg = syn.MNIST_PARAMS
+    m = _fill(_mod("models.controlnet").ControlNet(cfg))
+    x, hint = inputs("config1", 16, 1, 28)
+    zs = [syn.det_noise(f"config1:z{k}", tuple(x.shape)) for k in range(50)]
+    g = golden("config1_mnist_b16_50step")
+    sched = _mod("scheduler.linear_noise_scheduler").LinearNoiseScheduler(**syn.MNIST_DIFFUSION)
+    for mode in _modes(rt):
+        rt.set_mode(mode)
+        xt, x0 = _mod("sampler").DDPMSampler(m, sched, use_graph=False).sample_eager(x.cuda(), hint.cuda(), steps=50, zs=zs)
+        p, a = psnr(x0.cpu(), g["x0"]), max_abs(x0.cpu(), g["x0"])
+        assert p > X0_BOUND[mode]["psnr_db"] and a < X0_BOUND[mode]["max_abs"], (mode, p, a)
+        assert rel_l2(xt.cpu(), g["xt"]) < TRAJ_TOL[mode]
     assert rt.lib().cnb_tc_error_flag() == 0
 
 

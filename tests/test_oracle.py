@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import det_sd_for, golden, inputs, rel_l2, syn, ROOT
+from helpers import det_sd_for, golden, inputs, max_abs, psnr, rel_l2, syn, ROOT
 
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import cn_oracle as O  # noqa: E402
@@ -46,6 +46,21 @@ def test_controlnet_ddpm_vs_golden(name, cfg, B, ts):
             xt, x0 = O.ddpm_sample(lambda a, t, h: O.controlnet_ddpm_forward(sd, cfg, a, t, h), sched, x, hint, 3, zs)
             assert rel_l2(xt, g["traj3_xt"]) < 5 * TOL
             assert rel_l2(x0, g["traj3_x0"]) < 5 * TOL
+
+
+def test_config1_mnist_b16_50step_vs_golden():
+    """BASELINE.json configs[0] (MNIST ControlNet, batch 16, 50 steps, t = 49 .. 0): the oracle's final x_0 / x_{t-1}
+    against the unmodified reference's (tests/golden/config1_mnist_b16_50step.npz, oracle/make_golden.py)."""
+    cfg = syn.MNIST_PARAMS
+    sd = syn.det_state_dict(_keys_controlnet(cfg))
+    x, hint = inputs("config1", 16, cfg["im_channels"], cfg["im_size"])
+    g = golden("config1_mnist_b16_50step")
+    sched = O.SchedulerOracle(**syn.MNIST_DIFFUSION)
+    zs = [syn.det_noise(f"config1:z{k}", tuple(x.shape)) for k in range(50)]
+    with torch.no_grad():
+        xt, x0 = O.ddpm_sample(lambda a, t, h: O.controlnet_ddpm_forward(sd, cfg, a, t, h), sched, x, hint, 50, zs)
+    assert psnr(x0, g["x0"]) > 80.0 and max_abs(x0, g["x0"]) < 1e-3, (psnr(x0, g["x0"]), max_abs(x0, g["x0"]))
+    assert rel_l2(xt, g["xt"]) < 1e-4
 
 
 def test_controlnet_ldm_vs_golden():
