@@ -21,13 +21,16 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) {
+bool pdl_enabled(long long work) {
+  static int mode = -1;
+  static long long limit = 4ll << 20;
+  if (mode < 0) {
     const char* e = getenv("CNB_PDL");
-    v = e ? atoi(e) : 0;      // measured: no gain inside the replayed CUDA graph (14.20 vs 14.13 ms/step), so off by default
+    const char* w = getenv("CNB_PDL_WORK");
+    if (w) limit = atoll(w);
+    mode = e ? atoi(e) : 2;      // 0 = never, 1 = always, 2 = auto (short launches only; see common.cuh)
   }
-  return v != 0;
+  return mode == 1 || (mode == 2 && work <= limit);
 }
 
 int conv2d_f32(const cnb_conv_params* p, cudaStream_t st);

@@ -364,7 +364,7 @@ static int launch2(const void* qkv, void* out, int B, int L, int E, int heads, c
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)D);
   dim3 grid(ceil_div(L, 16 * NW), heads, B);
-  CNB_CUDA(launch_pdl(attention_f16_kernel<D, BK, NW, H2>, grid, dim3(NW * 32), SMEM, st,
+  CNB_CUDA(launch_pdl((long long)B * L * E, attention_f16_kernel<D, BK, NW, H2>, grid, dim3(NW * 32), SMEM, st,
                       reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(out), L, E, scale_log2));
   CNB_LAUNCH_CHECK();
   return CNB_OK;

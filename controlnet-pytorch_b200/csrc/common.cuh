@@ -59,11 +59,17 @@ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-bool pdl_enabled();   // api.cu: CNB_PDL=1 turns the launch attribute on (off: the device-side calls are no-ops)
+// api.cu.  `work` = output elements of the launch.  CNB_PDL=0 never, =1 always; default (auto): only for launches that
+// write at most CNB_PDL_WORK (4 Mi) elements.  Measured on the replayed MNIST step graph: always-on gains 7.6 % at
+// B = 16, 5.3 % at 64, 1.2 % at 256, nothing at 512 and LOSES 1 % at 1024 (12.74 vs 12.61 ms; also 12.82 ms when
+// only the 7x7 layers' launches at B = 1024, 6-13 Mi elements each, carry the attribute) - a dependent's CTAs parked
+// at griddepcontrol.wait take slots the other capture stream's kernels would have filled - so the attribute is set
+// only where the launch is short enough (under ~10 us) for its ramp-up and tail to matter.
+bool pdl_enabled(long long work);
 
 template <typename... KArgs, typename... Args>
-static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                                     Args... args) {
+static inline cudaError_t launch_pdl(long long work, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                     cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
@@ -72,7 +78,7 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled(work) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);

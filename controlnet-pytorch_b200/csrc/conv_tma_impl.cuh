@@ -608,7 +608,7 @@ static int launch_epi(const TmaArgs& a_in, int num_sms, cudaStream_t st) {
     a.epi_alt = alt_env >= 0 ? alt_env : ((a.halo && (long long)BN * ktot < 131072) ? 1 : 0);
   }
   smem_bytes = (size_t)a.bar_off + C::BAR_BYTES + 1024;
-  CNB_CUDA(launch_pdl(conv_tma_kernel<BN, HALF, EPI, RB>, dim3(grid), dim3(NUM_THREADS), smem_bytes, st, a));
+  CNB_CUDA(launch_pdl((long long)ntiles * 128 * BN, conv_tma_kernel<BN, HALF, EPI, RB>, dim3(grid), dim3(NUM_THREADS), smem_bytes, st, a));
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }

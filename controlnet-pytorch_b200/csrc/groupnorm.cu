@@ -382,7 +382,7 @@ static int launch_reg(const void* x, void* y, const float* gamma, const float* b
   cfg.numAttrs = 1;
   if (split == 1) {      // single-CTA samples: plain (non-cluster) launch that may overlap its predecessor's tail
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled((long long)B * HW * C) ? 1 : 0;
   }
   cudaError_t e;
   const int sel = (silu ? 4 : 0) | (out_f16 ? 2 : 0) | (in_f16 ? 1 : 0);
@@ -472,7 +472,7 @@ template <int KMAX, bool SILU, bool HALF, bool HIN>
 static void launch_warp_one(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
                             float eps, cudaStream_t st) {
   const int BG = B * G;
-  launch_pdl(groupnorm_warp_kernel<KMAX, SILU, HALF, HIN>, dim3(ceil_div(BG, 8)), dim3(256), 0, st, x, y, gamma, beta, BG,
+  launch_pdl((long long)B * HW * C, groupnorm_warp_kernel<KMAX, SILU, HALF, HIN>, dim3(ceil_div(BG, 8)), dim3(256), 0, st, x, y, gamma, beta, BG,
              HW, C, G, eps);
 }
 
@@ -513,10 +513,10 @@ static void launch_sweep(const void* x, void* y, const float* gamma, const float
                            110 * 1024);
       attr_set = true;
     }
-    launch_pdl(groupnorm_nhwc_kernel<SILU, HALF, HIN, HIN>, dim3(B), dim3(NT), staged, st, x, y, gamma, beta, HW, C, G,
+    launch_pdl((long long)B * HW * C, groupnorm_nhwc_kernel<SILU, HALF, HIN, HIN>, dim3(B), dim3(NT), staged, st, x, y, gamma, beta, HW, C, G,
                eps);
   } else {
-    launch_pdl(groupnorm_nhwc_kernel<SILU, HALF, HIN, false>, dim3(B), dim3(NT), smem, st, x, y, gamma, beta, HW, C, G,
+    launch_pdl((long long)B * HW * C, groupnorm_nhwc_kernel<SILU, HALF, HIN, false>, dim3(B), dim3(NT), smem, st, x, y, gamma, beta, HW, C, G,
                eps);
   }
 }
