@@ -3,7 +3,8 @@ models.* / scheduler.* modules on that path).  See DESIGN.md and INTEGRATION.md.
 
 The directory name carries a hyphen, so import it with
     importlib.import_module("controlnet-pytorch_b200")
-or put this directory itself first on sys.path and use the reference's own import lines
-(`from models.controlnet import ControlNet`, `from scheduler.linear_noise_scheduler import ...`).
+or put `dropin/` (shim packages `models` / `scheduler` that re-export the modules here) first on sys.path and use
+the reference's own import lines (`from models.controlnet import ControlNet`, `from scheduler.linear_noise_scheduler
+import ...`); see INTEGRATION.md section 1.
 """
 __all__ = ["models", "scheduler", "utils", "ops", "runtime"]

@@ -188,3 +188,43 @@ def test_gather_shards_gloo_world2(total):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def _dropin_env(extra_path=()):
+    env = dict(os.environ)
+    env["PYTHONSAFEPATH"] = "1"           # keep the cwd (a reference checkout has its own `models`) off sys.path
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "controlnet-pytorch_b200", "dropin"), *extra_path])
+    return env
+
+
+def test_dropin_shim_serves_the_reference_import_lines(tmp_path):
+    """with controlnet-pytorch_b200/dropin first on sys.path the reference's import lines
+    (`from models.controlnet import ControlNet`, ...) resolve to the B200 classes."""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_tool_loop.py"), "--check-imports"],
+                       env=_dropin_env(), cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "dropin imports ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tools"), reason="needs the reference checkout")
+def test_reference_tools_import_the_dropins_and_keep_their_other_modules():
+    """The unmodified tools/sample_*.py, run from the reference checkout, get the B200 models / scheduler while
+    dataset.*, scheduler.consistency_scheduler and models.discriminator still come from the reference."""
+    import subprocess
+    code = (
+        "import tools.sample_ddpm_controlnet as t, tools.sample_ldm_controlnet as l\n"
+        "import tools.sample_consistency_controlnet_distilled as c\n"
+        "import tools.sample_distribution_matching_controlnet_distilled as d\n"
+        "import scheduler.consistency_scheduler as cs, models.discriminator as md\n"
+        "P = 'controlnet-pytorch_b200.'\n"
+        "assert t.ControlNet.__module__ == P + 'models.controlnet'\n"
+        "assert t.LinearNoiseScheduler.__module__ == P + 'scheduler.linear_noise_scheduler'\n"
+        "assert l.ControlNet.__module__ == P + 'models.controlnet_ldm' and l.VAE.__module__ == P + 'models.vae'\n"
+        "assert c.ConsistencyControlNetDistilled.__module__ == P + 'models.consistency_controlnet_distilled'\n"
+        "assert d.DistributionMatchingControlNetDistilled.__module__ == P + 'models.distribution_matching_controlnet'\n"
+        "assert cs.__file__.startswith('/root/reference/') and md.__file__.startswith('/root/reference/')\n"
+        "assert t.MnistDataset.__module__ == 'dataset.mnist_dataset'\n"
+        "print('tools ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], env=_dropin_env(["/root/reference"]), cwd="/root/reference",
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "tools ok" in r.stdout, r.stdout + r.stderr

@@ -399,3 +399,16 @@ def test_split_stream_sampler_is_bit_identical(rt, monkeypatch):
     for split in ("1", "2", "3"):
         assert torch.equal(outs[split][0], eager[0]) and torch.equal(outs[split][1], eager[1]), split
     assert rt.lib().cnb_tc_error_flag() == 0
+
+
+def test_dropin_shim_runs_the_reference_tool_loop(rt, tmp_path):
+    """the reference tool's import lines and sampling loop (tools/sample_ddpm_controlnet.py
+    :9-12, :43-51), run in a fresh interpreter with controlnet-pytorch_b200/dropin first on sys.path, execute on the
+    B200 kernels and reproduce the reference's 3-step fixture (tests/dropin_tool_loop.py)."""
+    import subprocess
+    env = dict(os.environ)
+    env["PYTHONSAFEPATH"] = "1"
+    env["PYTHONPATH"] = os.path.join(ROOT, "controlnet-pytorch_b200", "dropin")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "dropin_tool_loop.py")], env=env, cwd=str(tmp_path),
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "dropin tool loop" in r.stdout, r.stdout + r.stderr
