@@ -12,12 +12,14 @@ from . import _engine as E
 
 
 def build_hint_block(hint_channels, c0, zero_tail):
-    tail = nn.Conv2d(c0, c0, kernel_size=1, padding=0)
+    # layers are created in the reference's order so that seeded default initialisation draws the same numbers
+    seq = nn.Sequential(nn.Conv2d(hint_channels, 64, kernel_size=3, padding=1), nn.SiLU(),
+                        nn.Conv2d(64, 128, kernel_size=3, padding=1), nn.SiLU(),
+                        nn.Conv2d(128, c0, kernel_size=3, padding=1), nn.SiLU(),
+                        nn.Conv2d(c0, c0, kernel_size=1, padding=0))
     if zero_tail:
-        E.zero_(tail)
-    return nn.Sequential(nn.Conv2d(hint_channels, 64, kernel_size=3, padding=1), nn.SiLU(),
-                         nn.Conv2d(64, 128, kernel_size=3, padding=1), nn.SiLU(),
-                         nn.Conv2d(128, c0, kernel_size=3, padding=1), nn.SiLU(), tail)
+        E.zero_(seq[6])
+    return seq
 
 
 def student_body(model, x_nhwc, t_index, hint, mode):

@@ -228,3 +228,88 @@ def test_reference_tools_import_the_dropins_and_keep_their_other_modules():
     r = subprocess.run([sys.executable, "-c", code], env=_dropin_env(["/root/reference"]), cwd="/root/reference",
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "tools ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="needs the reference checkout")
+def test_checkpoints_written_by_the_reference_load_the_way_the_tools_load_them(tmp_path):
+    """The construction / checkpoint sequences of tools/sample_ddpm_controlnet.py:80-92,
+    tools/sample_consistency_controlnet_distilled.py:30-49 and
+    tools/sample_distribution_matching_controlnet_distilled.py:33-54, fed with files written by the REFERENCE classes:
+    every tensor of the resulting B200 module equals the reference module built the same way."""
+    cfg = syn.TINY_PARAMS
+    ddpm, ctrl = str(tmp_path / "ddpm_ckpt.pth"), str(tmp_path / "controlnet_ckpt.pth")
+    cons, dmck = str(tmp_path / "consistency.pth"), str(tmp_path / "dm.pth")
+    purge = lambda: [sys.modules.pop(k) for k in list(sys.modules)          # noqa: E731
+                     if k.split(".")[0] in ("models", "scheduler")]
+    sys.path.insert(0, "/root/reference")
+    try:
+        purge()
+        from models.unet_base import Unet as RefUnet
+        from models.controlnet import ControlNet as RefCN
+        from models.consistency_controlnet_distilled import ConsistencyControlNetDistilled as RefCons
+        from models.distribution_matching_controlnet import DistributionMatchingControlNetDistilled as RefDM
+        torch.manual_seed(11)
+        torch.save(RefUnet(cfg).state_dict(), ddpm)
+        torch.manual_seed(20)
+        ref_cn = RefCN(cfg, model_ckpt=ddpm, device=torch.device("cpu"))
+        ref_cn.load_state_dict(syn.det_state_dict(ref_cn.state_dict(), seed=5))
+        torch.save(ref_cn.state_dict(), ctrl)
+        torch.manual_seed(21)
+        ref_cons = RefCons(cfg, ddpm, device=torch.device("cpu"))
+        torch.save({"model_state_dict": syn.det_state_dict(ref_cons.student.state_dict(), seed=6)}, cons)
+        ref_cons.student.load_state_dict(torch.load(cons, weights_only=False)["model_state_dict"])
+        torch.manual_seed(22)
+        ref_dm = RefDM(cfg, ctrl, device=torch.device("cpu"))
+        torch.save({"model_state_dict": syn.det_state_dict(ref_dm.student.state_dict(), seed=7)}, dmck)
+        ref_dm.student.load_state_dict(torch.load(dmck, weights_only=False)["model_state_dict"])
+        want = {"cn": ref_cn.state_dict(), "cons": ref_cons.state_dict(), "dm": ref_dm.state_dict()}
+    finally:
+        sys.path.remove("/root/reference")
+        purge()
+    dev = torch.device("cpu")
+    torch.manual_seed(20)
+    cn = _mod("models.controlnet").ControlNet(cfg, model_ckpt=ddpm, device=dev).to(dev)
+    cn.load_state_dict(torch.load(ctrl, map_location=dev))
+    torch.manual_seed(21)       # same seed as the reference construction: the unloaded tensors (hint blocks) match too
+    mc = _mod("models.consistency_controlnet_distilled").ConsistencyControlNetDistilled(cfg, ddpm, device=dev).to(dev)
+    mc.student.load_state_dict(torch.load(cons, map_location=dev, weights_only=False)["model_state_dict"])
+    torch.manual_seed(22)
+    md = _mod("models.distribution_matching_controlnet").DistributionMatchingControlNetDistilled(cfg, ctrl, device=dev).to(dev)
+    md.student.load_state_dict(torch.load(dmck, map_location=dev, weights_only=False)["model_state_dict"])
+    for tag, mine in (("cn", cn.state_dict()), ("cons", mc.state_dict()), ("dm", md.state_dict())):
+        ref = want[tag]
+        assert list(mine) == list(ref), (tag, set(mine) ^ set(ref))
+        for k in ref:
+            assert torch.equal(mine[k], ref[k]), (tag, k)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="needs the reference checkout")
+def test_every_dropin_class_initialises_seed_identically_to_the_reference():
+    """torch.manual_seed(s) + constructor gives the same tensors under the same keys as the reference class, for every
+    module on the path (layers are created in the reference's order, so the default initialisers draw the same numbers)."""
+    specs = [("models.controlnet_ldm", "ControlNet", (4, syn.TINY_LDM_PARAMS), dict(down_sample_factor=8)),
+             ("models.vae", "VAE", (3, syn.TINY_VAE_PARAMS), {}),
+             ("models.unet_base", "Unet", (syn.TINY_PARAMS,), {}),
+             ("models.unet_cond_base", "Unet", (4, syn.TINY_LDM_PARAMS), {}),
+             ("models.consistency_controlnet_distilled", "ConsistencyControlNet", (syn.TINY_PARAMS,), {}),
+             ("models.consistency_controlnet_distilled", "ConsistencyControlNetDistilled", (syn.TINY_PARAMS,), {}),
+             ("models.distribution_matching_controlnet", "DistributionMatchingControlNet", (syn.TINY_PARAMS,), {}),
+             ("models.controlnet", "ControlNet", (syn.MNIST_PARAMS,), {})]
+    mine = []
+    for i, (mod, cls, a, k) in enumerate(specs):
+        torch.manual_seed(100 + i)
+        mine.append(getattr(_mod(mod), cls)(*a, **k).state_dict())
+    purge = lambda: [sys.modules.pop(k) for k in list(sys.modules)          # noqa: E731
+                     if k.split(".")[0] in ("models", "scheduler")]
+    sys.path.insert(0, "/root/reference")
+    try:
+        purge()
+        for i, (mod, cls, a, k) in enumerate(specs):
+            torch.manual_seed(100 + i)
+            ref = getattr(importlib.import_module(mod), cls)(*a, **k).state_dict()
+            assert list(mine[i]) == list(ref), (mod, cls)
+            for name in ref:
+                assert torch.equal(mine[i][name], ref[name]), (mod, cls, name)
+    finally:
+        sys.path.remove("/root/reference")
+        purge()
