@@ -313,3 +313,46 @@ def test_every_dropin_class_initialises_seed_identically_to_the_reference():
     finally:
         sys.path.remove("/root/reference")
         purge()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="needs the reference checkout")
+def test_public_surface_matches_the_reference_signatures():
+    """Every public class / function of the reference's hot-path modules exists in the drop-in module, and the
+    inference-side methods take the reference's parameters (names, order, defaults); extra trailing keyword
+    parameters (`z=`, `step_index=`) are allowed."""
+    import inspect
+    mods = ["models.unet_base", "models.blocks", "models.unet_cond_base", "models.controlnet", "models.controlnet_ldm",
+            "models.consistency_controlnet_distilled", "models.distribution_matching_controlnet", "models.vae",
+            "scheduler.linear_noise_scheduler"]
+    methods = ("__init__", "forward", "encode", "decode", "generate", "sample_prev_timestep", "add_noise", "get_params",
+               "get_teacher_prediction", "get_ddpm_teacher_prediction", "sigma_to_timestep", "get_noise_schedule",
+               "c_skip", "c_out", "c_in", "c_noise")
+    ours = {m: _mod(m) for m in mods}
+    purge = lambda: [sys.modules.pop(k) for k in list(sys.modules)          # noqa: E731
+                     if k.split(".")[0] in ("models", "scheduler")]
+    params = lambda f: [(p.name, p.default) for p in inspect.signature(f).parameters.values()]   # noqa: E731
+    sys.path.insert(0, "/root/reference")
+    checked = 0
+    try:
+        purge()
+        for m in mods:
+            ref = importlib.import_module(m)
+            for name, obj in vars(ref).items():
+                if name.startswith("_") or getattr(obj, "__module__", None) != m:
+                    continue
+                mine = getattr(ours[m], name, None)
+                assert mine is not None, (m, name)
+                if inspect.isclass(obj):
+                    for meth in methods:
+                        if meth in vars(obj):
+                            want, got = params(getattr(obj, meth)), params(getattr(mine, meth))
+                            assert got[:len(want)] == want, (m, name, meth, want, got)
+                            checked += 1
+                elif inspect.isfunction(obj):
+                    want, got = params(obj), params(mine)
+                    assert got[:len(want)] == want, (m, name, want, got)
+                    checked += 1
+    finally:
+        sys.path.remove("/root/reference")
+        purge()
+    assert checked >= 40
