@@ -356,3 +356,33 @@ def test_public_surface_matches_the_reference_signatures():
         sys.path.remove("/root/reference")
         purge()
     assert checked >= 40
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="needs the reference checkout")
+def test_host_side_helpers_are_bit_identical_to_the_reference():
+    """add_noise (linear_noise_scheduler.py:25-47), the EDM scalings (consistency_controlnet_distilled.py:45-74) and the
+    Karras schedule (:175-196) are plain host tensor expressions in both implementations: bit-identical on the CPU."""
+    s = _mod("scheduler.linear_noise_scheduler").LinearNoiseScheduler(**syn.MNIST_DIFFUSION)
+    g = torch.Generator().manual_seed(0)
+    x, n = torch.randn(4, 1, 8, 8, generator=g), torch.randn(4, 1, 8, 8, generator=g)
+    t, sig = torch.tensor([0, 5, 500, 999]), torch.tensor([0.002, 1.7, 80.0])
+    cc = _mod("models.consistency_controlnet_distilled")
+    cm, cd = cc.ConsistencyControlNet(syn.TINY_PARAMS), cc.ConsistencyControlNetDistilled(syn.TINY_PARAMS)
+    mine = [s.add_noise(x, n, t), cm.c_skip(sig), cm.c_out(sig), cm.c_in(sig), cm.c_noise(sig),
+            cd.get_noise_schedule(10, device=torch.device("cpu"))]
+    purge = lambda: [sys.modules.pop(k) for k in list(sys.modules)          # noqa: E731
+                     if k.split(".")[0] in ("models", "scheduler")]
+    sys.path.insert(0, "/root/reference")
+    try:
+        purge()
+        from scheduler.linear_noise_scheduler import LinearNoiseScheduler as RefS
+        from models.consistency_controlnet_distilled import ConsistencyControlNet as RC, \
+            ConsistencyControlNetDistilled as RCD
+        r, rc = RefS(**syn.MNIST_DIFFUSION), RC(syn.TINY_PARAMS)
+        ref = [r.add_noise(x, n, t), rc.c_skip(sig), rc.c_out(sig), rc.c_in(sig), rc.c_noise(sig),
+               RCD(syn.TINY_PARAMS).get_noise_schedule(10, device=torch.device("cpu"))]
+    finally:
+        sys.path.remove("/root/reference")
+        purge()
+    for i, (a, b) in enumerate(zip(mine, ref)):
+        assert torch.equal(a, b), i
