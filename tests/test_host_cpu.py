@@ -386,3 +386,29 @@ def test_host_side_helpers_are_bit_identical_to_the_reference():
         purge()
     for i, (a, b) in enumerate(zip(mine, ref)):
         assert torch.equal(a, b), i
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="needs the reference checkout")
+@pytest.mark.parametrize("locked", [True, False])
+def test_model_locked_and_get_params_match_the_reference(locked):
+    """`model_locked` freezes the same parameters and `get_params()` (controlnet.py:140-156, controlnet_ldm.py) returns
+    the same parameters in the same order as the reference."""
+    def describe(m):
+        names = {id(p): n for n, p in m.named_parameters()}
+        return {n: p.requires_grad for n, p in m.named_parameters()}, [names[id(p)] for p in m.get_params()]
+    mine = [describe(_mod("models.controlnet").ControlNet(syn.TINY_PARAMS, model_locked=locked)),
+            describe(_mod("models.controlnet_ldm").ControlNet(4, syn.TINY_LDM_PARAMS, model_locked=locked,
+                                                              down_sample_factor=8))]
+    purge = lambda: [sys.modules.pop(k) for k in list(sys.modules)          # noqa: E731
+                     if k.split(".")[0] in ("models", "scheduler")]
+    sys.path.insert(0, "/root/reference")
+    try:
+        purge()
+        from models.controlnet import ControlNet as RefCN
+        from models.controlnet_ldm import ControlNet as RefLDM
+        ref = [describe(RefCN(syn.TINY_PARAMS, model_locked=locked)),
+               describe(RefLDM(4, syn.TINY_LDM_PARAMS, model_locked=locked, down_sample_factor=8))]
+    finally:
+        sys.path.remove("/root/reference")
+        purge()
+    assert mine == ref
