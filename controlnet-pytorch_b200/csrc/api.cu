@@ -108,7 +108,7 @@ extern "C" int cnb_conv2d(const cnb_conv_params* p, cnb_stream_t stream) {
   }
   // tiny-channel ends of the U-Net (Cin <= 4 or Cout <= 4): direct exact-fp32 kernels in every mode
   if (small_on && (p->Cin <= 4 || p->Cout <= 4) && conv2d_small_supported(p)) return conv2d_small(p, st);
-  if (p->mode == CNB_MODE_TF32 || p->mode == CNB_MODE_BF16) {
+  if (p->mode == CNB_MODE_F16) {
     if (conv2d_tma_supported(p)) return conv2d_tma(p, st);     // TMA-im2col fed persistent tcgen05 kernel
     if (conv2d_tc_supported(p)) return conv2d_tc(p, st);       // cp.async-gather tcgen05 kernel (narrow Cin)
   } else if (p->mode != CNB_MODE_F32) {

@@ -356,11 +356,10 @@ template <int D, int BK, int NW, bool H2>
 static int launch2(const void* qkv, void* out, int B, int L, int E, int heads, cudaStream_t st) {
   constexpr int DP = (D + 15) / 16 * 16;
   constexpr size_t SMEM = (size_t)3 * attn_sub(D, BK, NW) * 2 * BK * (DP + 8) * sizeof(__half);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     CNB_CUDA(cudaFuncSetAttribute(attention_f16_kernel<D, BK, NW, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)SMEM));
-    attr_set = true;
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)D);
   dim3 grid(ceil_div(L, 16 * NW), heads, B);

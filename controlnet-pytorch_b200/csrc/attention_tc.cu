@@ -194,10 +194,9 @@ attention_tf32_kernel(const float* __restrict__ qkv, float* __restrict__ out, in
 template <int D, int BKEYS>
 static int launch(const float* qkv, float* out, int B, int L, int E, int heads, int d_real, cudaStream_t st) {
   constexpr size_t SMEM = (size_t)2 * 2 * BKEYS * (D + 4) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     CNB_CUDA(cudaFuncSetAttribute(attention_tf32_kernel<D, BKEYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    attr_set = true;
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)d_real);
   dim3 grid(ceil_div(L, BQ), heads, B);

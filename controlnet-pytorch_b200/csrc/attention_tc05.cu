@@ -516,10 +516,9 @@ static int launch(const void* qkv, void* out, int B, int L, int E, int heads, cu
     }
     g_encode = reinterpret_cast<EncodeTiledFn>(f);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     CNB_CUDA(cudaFuncSetAttribute(attention_tc05_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set = true;
   }
   Args a;
   memset(&a, 0, sizeof(a));

@@ -50,6 +50,21 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Function attributes (MaxDynamicSharedMemorySize) are PER DEVICE: a process that touches cuda:1 after cuda:0 must set
+// them again there.  `static DeviceOnce once; if (once.first()) cudaFuncSetAttribute(...)` at each launch site.
+// (Device PROPERTIES cached process-wide - SM count, tcgen05 availability - assume the homogeneous GPUs of one box.)
+struct DeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) return true;
+    d &= 63;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 // ---- programmatic dependent launch (PDL) -------------------------------------------------------------------
 // Kernels launched through launch_pdl() may start while their predecessor in the stream is still draining: they run
 // their prologue (barrier init, TMEM allocation, descriptor fetch, index math), then pdl_wait() blocks until the

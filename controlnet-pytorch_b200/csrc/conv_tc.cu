@@ -1,4 +1,4 @@
-// tcgen05 implicit-GEMM convolution (CNB_MODE_TF32): the tensor-core path of cnb_conv2d on sm_100a.
+// tcgen05 implicit-GEMM convolution (CNB_MODE_F16): the tensor-core path of cnb_conv2d on sm_100a.
 //
 //   GEMM view        M = B*OH*OW output pixels (tile 128 = one UMMA M),  N = Cout (tile BN in {16,...,256}),
 //                    K = ntaps*Cin (tile = one 128-byte swizzle row: 32 fp32 (kind::tf32) or 64 fp16 (kind::f16)).
@@ -284,10 +284,9 @@ conv_igemm_tc_kernel(const __grid_constant__ TcArgs a) {
 template <int BN, int S, bool HALF>
 static int launch_tc(const TcArgs& a, cudaStream_t st) {
   using L = SmemLayout<BN, S>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     CNB_CUDA(cudaFuncSetAttribute(conv_igemm_tc_kernel<BN, S, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
   }
   dim3 grid(ceil_div(a.M, BM), ceil_div(a.p.Cout, BN));
   conv_igemm_tc_kernel<BN, S, HALF><<<grid, 160, L::TOTAL, st>>>(a);

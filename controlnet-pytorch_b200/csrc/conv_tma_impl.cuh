@@ -526,11 +526,10 @@ inline int g_bres_enabled() {
 template <int BN, bool HALF, int EPI, int RB>
 static int launch_epi(const TmaArgs& a_in, int num_sms, cudaStream_t st) {
   using C = Cfg<BN, RB>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     CNB_CUDA(cudaFuncSetAttribute(conv_tma_kernel<BN, HALF, EPI, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   SMEM_BUDGET));
-    attr_set = true;
   }
   TmaArgs a = a_in;
   const int ntiles = a.tiles_m * a.tiles_n;

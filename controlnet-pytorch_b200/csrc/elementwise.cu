@@ -229,12 +229,20 @@ __global__ void scale_rows_kernel(const float* __restrict__ a, const float* __re
 // order as the reference (mul, sub, div, clamp), no FMA contraction: bit-identical to the fp32 ATen expression.
 __global__ void x0_from_eps_kernel(const float* __restrict__ xt, const float* __restrict__ eps,
                                    const float* __restrict__ sqrt_one_minus, const float* __restrict__ sqrt_alpha,
-                                   const long long* __restrict__ t, int t_count, float* __restrict__ out,
-                                   long long per_sample, long long total) {
+                                   const long long* __restrict__ t, int t_count, int num_timesteps,
+                                   float* __restrict__ out, long long per_sample, long long total) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int b = (int)(i / per_sample);
-  const long long tb = t[t_count == 1 ? 0 : b];
+  long long tb = t[t_count == 1 ? 0 : b];
+  // torch indexing semantics of `table[t]`: negative indices wrap once, anything else out of range is an error - the
+  // reference raises IndexError on the host; a device kernel cannot, so the sample is poisoned with NaN instead of
+  // reading outside the tables
+  if (tb < 0) tb += num_timesteps;
+  if (tb < 0 || tb >= num_timesteps) {
+    out[i] = __int_as_float(0x7fc00000);
+    return;
+  }
   const float v = __fdiv_rn(__fsub_rn(xt[i], __fmul_rn(sqrt_one_minus[tb], eps[i])), sqrt_alpha[tb]);
   out[i] = fminf(fmaxf(v, -1.0f), 1.0f);
 }
@@ -313,11 +321,6 @@ __global__ void pack_convT_weight_kernel(const float* __restrict__ w, float* __r
   int kx = px == 0 ? (tb == 0 ? 1 : 3) : (tb == 0 ? 0 : 2);
   float v = w[(((long long)c * O + o) * 4 + ky) * 4 + kx];
   dst[i] = rtf32 ? round_tf32(v) : v;
-}
-
-__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
 }
 
 __global__ void cast_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
@@ -426,7 +429,8 @@ extern "C" int cnb_x0_from_eps(const float* xt, const float* eps, const float* s
   CNB_REQUIRE(xt && eps && sqrt_one_minus && sqrt_alpha && t && out && total > 0 && (t_count == 1 || t_count == B) &&
                   num_timesteps > 0, "x0_from_eps: bad args");
   x0_from_eps_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)s>>>(
-      xt, eps, sqrt_one_minus, sqrt_alpha, reinterpret_cast<const long long*>(t), t_count, out, per_sample, total);
+      xt, eps, sqrt_one_minus, sqrt_alpha, reinterpret_cast<const long long*>(t), t_count, num_timesteps, out, per_sample,
+      total);
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }
@@ -488,13 +492,6 @@ extern "C" int cnb_pack_convT_weight(const float* w, float* dst, int I, int O, i
   long long total = (long long)I * O * 16;
   CNB_REQUIRE(total > 0, "pack_convT_weight: bad dims");
   pack_convT_weight_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)s>>>(w, dst, I, O, round_tf32, total);
-  CNB_LAUNCH_CHECK();
-  return CNB_OK;
-}
-
-extern "C" int cnb_cast_bf16(const float* src, void* dst, long long n, cnb_stream_t s) {
-  CNB_REQUIRE(n > 0, "cast_bf16: n=%lld", n);
-  cast_bf16_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)s>>>(src, (__nv_bfloat16*)dst, n);
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }

@@ -507,11 +507,10 @@ static void launch_sweep(const void* x, void* y, const float* gamma, const float
   const size_t slab = (size_t)HW * C * 2;                  // fp16 slab
   const size_t staged = (smem + 127) / 128 * 128 + slab;
   if (HIN && g_gn_stage && slab % 16 == 0 && slab < (1u << 20) && staged <= 110 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    if (attr_once.first()) {
       cudaFuncSetAttribute(groupnorm_nhwc_kernel<SILU, HALF, HIN, HIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            110 * 1024);
-      attr_set = true;
     }
     launch_pdl((long long)B * HW * C, groupnorm_nhwc_kernel<SILU, HALF, HIN, HIN>, dim3(B), dim3(NT), staged, st, x, y, gamma, beta, HW, C, G,
                eps);

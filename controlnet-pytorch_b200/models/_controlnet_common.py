@@ -46,6 +46,7 @@ def controlnet_forward(trained, control, down_zero, mid_zero, hint_feat_fn, x, t
     mode = rt.get_mode()
     dev = x.device
     xn = ops.nchw_to_nhwc(x)
+    t = E.check_t(t, x.shape[0], dev)
 
     plan_t = E.temb_plan(trained, E.unet_time(trained, t, dev))
     plan_c = E.temb_plan(control, E.unet_time(control, t, dev), with_ups=False)

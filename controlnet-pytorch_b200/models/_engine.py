@@ -169,6 +169,16 @@ def as_t(t, device):
     return t.contiguous()
 
 
+def check_t(t, batch, device):
+    """t as the kernels want it, with the shape rule the reference enforces by broadcasting: one row for the whole batch
+    ((1,) / 0-d, the sampling tools) or one per sample ((B,), training / compare / student tools).  Anything else is the
+    reference's broadcast RuntimeError (`out + t_emb_layers(t_emb)[:, :, None, None]`, unet_base.py:98)."""
+    t = as_t(t, device)
+    if t.dim() != 1 or t.numel() not in (1, batch):
+        raise RuntimeError("The size of tensor t (%d) must match the batch size (%d) or be 1" % (t.numel(), batch))
+    return t
+
+
 def sinusoid(t, dim, device):
     assert dim % 2 == 0, "time embedding dimension must be divisible by 2"
     return ops.time_embedding(as_t(t, device), temb_factor(dim, device), dim)
@@ -466,22 +476,39 @@ def hint_stack_ddpm(seq, hint_nhwc, mode):
 class HintCache:
     """hint_block(hint) depends on neither t nor x (controlnet.py:179): compute once per (hint storage, weights).
     A few entries are kept (the split sampler runs batch halves of one hint tensor on parallel streams); every entry
-    holds a reference to its hint tensor, so the storage cannot be recycled under the cached key."""
+    holds a reference to its hint tensor, so the storage cannot be recycled under the cached key.
+
+    An entry is keyed by the hint's STORAGE (data_ptr, shape, strides), the mode and the hint-block weights; the hint's
+    version counter is a stamp inside the entry.  When the same storage is overwritten in place (the way a captured
+    CUDA graph is re-used with a new hint) the feature is recomputed INTO THE SAME feature tensor, so a graph that baked
+    that tensor's address keeps reading valid, current data (sampler.DDPMSampler calls `refresh` before every replay).
+    Recomputing under stream capture would silently bake a one-off update into the graph, so it raises instead."""
     MAX_ENTRIES = 8
 
     def __init__(self):
         self.entries = {}
 
     def get(self, hint, params, mode, fn):
-        key = (hint.data_ptr(), hint._version, tuple(hint.shape), tuple(hint.stride()), mode,
+        key = (hint.data_ptr(), tuple(hint.shape), tuple(hint.stride()), mode,
                tuple((p._version, p.data_ptr()) for p in params))
         ent = self.entries.get(key)
         if ent is None:
             if len(self.entries) >= self.MAX_ENTRIES:
                 self.entries.pop(next(iter(self.entries)))
-            ent = (hint, fn())
+            ent = [hint, hint._version, fn()]
             self.entries[key] = ent
-        return ent[1]
+        elif ent[1] != hint._version:
+            if torch.cuda.is_current_stream_capturing():
+                raise rt.CnbError("hint tensor was modified in place between warm-up and CUDA-graph capture")
+            with torch.no_grad():
+                ent[2].copy_(fn())
+            ent[1] = hint._version
+        return ent[2]
+
+    def pinned(self):
+        """The (hint, feature) tensors of every live entry: a sampler that captured them into a graph keeps these
+        references so that eviction cannot free memory the graph still reads."""
+        return [(e[0], e[2]) for e in self.entries.values()]
 
     def clear(self):
         self.entries = {}

@@ -25,6 +25,7 @@ def build_hint_block(hint_channels, c0, zero_tail):
 def student_body(model, x_nhwc, t_index, hint, mode):
     """x_nhwc: channels-last input already scaled; t_index: int64 CUDA (B,) or (1,).  Returns channels-last output."""
     unet = model.unet
+    t_index = E.check_t(t_index, x_nhwc.shape[0], x_nhwc.device)
     emb = E.sinusoid(t_index, model.t_emb_dim, x_nhwc.device)
     lin = model.t_proj[1]
     temb = ops.linear_small(emb, E.raw(lin.weight), E.raw(lin.bias), silu_in=True)

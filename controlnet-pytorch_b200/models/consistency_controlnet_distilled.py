@@ -11,6 +11,7 @@ import torch.nn as nn
 from .. import ops
 from .. import runtime as rt
 from . import _engine as E
+from ._entry import host_entry
 from ._student_common import build_hint_block, student_body
 from .controlnet import ControlNet
 from .unet_base import Unet
@@ -52,6 +53,7 @@ class ConsistencyControlNet(nn.Module):
             sigma = torch.tensor(sigma, dtype=torch.float32)
         return 0.25 * torch.log(sigma.clamp(min=1e-8))
 
+    @host_entry
     def forward(self, x_t, sigma, hint):
         """x0 = c_skip(sigma) x_t + c_out(sigma) F(c_in(sigma) x_t, t(sigma), hint); returns x_t itself when
         all(sigma <= sigma_min) (:81-82).  sigma: float tensor, 0-d / (B,) / (B,1,1,1)."""

@@ -7,6 +7,7 @@ import torch
 import torch.nn as nn
 
 from . import _engine as E
+from ._entry import host_entry
 from ._controlnet_common import controlnet_forward, split_prefix
 from .unet_base import Unet, get_time_embedding  # noqa: F401
 
@@ -74,6 +75,7 @@ class ControlNet(nn.Module):
         return self._hint_cache.get(hint, list(seq.parameters()), mode,
                                     lambda: E.hint_stack_ddpm(seq, ops.nchw_to_nhwc(hint), mode))
 
+    @host_entry
     def forward(self, x, t, hint):
         """eps = ControlNet(x_t, t, hint); x (B,C,H,W), hint (B,hint_channels,H,W) fp32 CUDA; t int (1,) or (B,)."""
         return controlnet_forward(self.trained_unet, self.control_copy_unet, self.control_copy_unet_down_zero_convs,

@@ -7,6 +7,7 @@ import torch.nn as nn
 
 from .. import ops
 from . import _engine as E
+from ._entry import host_entry
 from ._controlnet_common import controlnet_forward
 from .blocks import get_time_embedding  # noqa: F401
 from .unet_cond_base import Unet
@@ -78,6 +79,7 @@ class ControlNet(nn.Module):
         return self._hint_cache.get(hint, list(seq.parameters()), mode,
                                     lambda: self._pyramid(ops.nchw_to_nhwc(hint), mode))
 
+    @host_entry
     def forward(self, x, t, hint):
         return controlnet_forward(self.trained_unet, self.control_unet, self.control_unet_down_zero_convs,
                                   self.control_unet_mid_zero_convs, self._hint_feat, x, t, hint)

@@ -10,6 +10,7 @@ import torch.nn as nn
 from .. import ops
 from .. import runtime as rt
 from . import _engine as E
+from ._entry import host_entry
 from ._student_common import build_hint_block, student_body
 from .controlnet import ControlNet
 from .unet_base import Unet, get_time_embedding  # noqa: F401
@@ -57,6 +58,7 @@ class DistributionMatchingControlNet(nn.Module):
         self.t_proj = E.act_linear(self.t_emb_dim, self.t_emb_dim)
         self._hint_cache = E.HintCache()
 
+    @host_entry
     def forward(self, x_t, t, hint):
         """x0 = student(x_t, t, hint): the output IS the sample (:155-157).  t: int scalar / (1,) / (B,)."""
         x_t = E._check_x(x_t)

@@ -10,6 +10,7 @@ import torch.nn as nn
 from .. import ops
 from .. import runtime as rt
 from . import _engine as E
+from ._entry import host_entry
 
 _GROUPS = 8
 
@@ -104,11 +105,12 @@ class Unet(nn.Module):
             self.norm_out = nn.GroupNorm(_GROUPS, 16)
             self.conv_out = nn.Conv2d(16, c['im_channels'], kernel_size=3, padding=1)
 
+    @host_entry
     def forward(self, x, t):
         """x (B, C, H, W) fp32 CUDA, t int (1,) or (B,) -> eps with x's shape (unet_base.py:341-374)."""
         x = E._check_x(x)
         mode = rt.get_mode()
-        temb = E.unet_time(self, t, x.device)
+        temb = E.unet_time(self, E.check_t(t, x.shape[0], x.device), x.device)
         plan = E.temb_plan(self, temb)
         h = E.conv_in(self, ops.nchw_to_nhwc(x), mode)
         return ops.nhwc_to_nchw(E.run_unet_body(self, h, plan, mode))

@@ -7,6 +7,7 @@ import torch.nn as nn
 from .. import ops
 from .. import runtime as rt
 from . import _engine as E
+from ._entry import host_entry
 from .blocks import DownBlock, MidBlock, UpBlockUnet
 
 
@@ -52,6 +53,7 @@ class Unet(nn.Module):
             self.norm_out = nn.GroupNorm(G, self.conv_out_channels)
             self.conv_out = nn.Conv2d(self.conv_out_channels, im_channels, kernel_size=3, padding=1)
 
+    @host_entry
     def forward(self, x, t, cond_input=None):
         x = E._check_x(x)
         mode = rt.get_mode()

@@ -47,10 +47,31 @@ class DDPMSampler:
         return xt, x0
 
     # ---- graph-replayed loop ----------------------------------------------------------------------------
+    def _param_stamp(self):
+        """(version, address) of every parameter: a load_state_dict / optimizer step / .to() after capture changes it,
+        and the graph (which baked the packed-weight caches derived from the old values) is rebuilt."""
+        return tuple((p._version, p.data_ptr()) for p in self.model.parameters())
+
+    def _hint_parts(self):
+        return [self._hint[lo:hi] for lo, hi in self._bounds]
+
+    def _refresh_hint(self):
+        """The captured step reads the hint FEATURE tensors the warm-up cached (models/_engine.HintCache); after the
+        static hint buffer has been overwritten they are recomputed in place, outside the graph, once per call."""
+        fn = getattr(self.model, "_hint_feat", None)
+        if fn is None:
+            return
+        mode = rt.get_mode()
+        for part in self._hint_parts():
+            fn(part, mode)
+
     def _capture(self, x_T, hint, steps, elem_offset):
         dev = x_T.device
         sch = self.scheduler
         self.xt = x_T.clone().contiguous()
+        # the graph reads a hint buffer OWNED by the sampler: callers may free or overwrite theirs
+        self._hint = hint.clone().contiguous()
+        hint = self._hint
         self.x0 = torch.empty_like(self.xt)
         self.t_seq = torch.arange(steps - 1, -1, -1, device=dev, dtype=torch.int64)
         self.step_idx = torch.zeros((1,), device=dev, dtype=torch.int32)
@@ -72,6 +93,7 @@ class DDPMSampler:
         nsplit = int(os.environ.get("CNB_SAMPLER_SPLIT", "2" if (big_model and B >= 128) else "1"))
         nsplit = max(1, min(nsplit, B))
         bounds = [shard_bounds(B, nsplit, k) for k in range(nsplit)]
+        self._bounds = bounds
         self._split_streams = [torch.cuda.Stream(device=dev) for _ in range(nsplit)] if nsplit > 1 else []
 
         def part(lo, hi):
@@ -98,6 +120,11 @@ class DDPMSampler:
         from .models import _controlnet_common as _cc
         _cc.set_branch_parallel(False if nsplit > 1 else None)
         try:
+            if nsplit > 1:
+                # cold caches: ONE unsplit forward on a single stream packs every weight / builds the t-embedding table
+                # before the parts (which only read those caches) run concurrently on the split streams
+                self.model(self.xt, self.t_seq[:1], hint)
+                torch.cuda.synchronize(dev)
             # warm-up on a side stream: builds weight / hint caches and sets kernel attributes outside the capture
             s = torch.cuda.Stream(device=dev)
             s.wait_stream(torch.cuda.current_stream())
@@ -114,6 +141,9 @@ class DDPMSampler:
             _cc.set_branch_parallel(None)
         self._graph = g
         self._nsteps, self._pos = steps, 0
+        # keep every tensor the graph reads alive for as long as the graph: the hint features (HintCache may evict)
+        cache = getattr(self.model, "_hint_cache", None)
+        self._baked = cache.pinned() if cache is not None else []
 
     @torch.no_grad()
     def sample(self, x_T, hint, steps=None, elem_offset=0):
@@ -122,13 +152,21 @@ class DDPMSampler:
         steps = self.scheduler.num_timesteps if steps is None else steps
         if not self.use_graph:
             return self.sample_eager(x_T, hint, steps, None, elem_offset)
-        key = (tuple(x_T.shape), hint.data_ptr(), tuple(hint.shape), steps, elem_offset, rt.get_mode(), str(x_T.device))
+        if hint.shape[0] != x_T.shape[0]:
+            raise rt.CnbError("sample: x_T and hint must have the same batch size")
+        key = (tuple(x_T.shape), tuple(hint.shape), steps, elem_offset, rt.get_mode(), str(x_T.device),
+               self._param_stamp())
         if self._graph is None or key != self._key:
             self._capture(x_T, hint, steps, elem_offset)
             self._key = key
+        else:
+            self._hint.copy_(hint)
+            self._refresh_hint()
         self.xt.copy_(x_T)
         self.replay_steps(steps, reset=True)
-        return self.xt.clone(), self.x0.clone()
+        out = self.xt.clone(), self.x0.clone()
+        check_device_errors()
+        return out
 
     def replay_steps(self, n, reset=True):
         """bench.py hook: replay the captured step n times (state continues from wherever it is)."""
@@ -161,6 +199,7 @@ class LDMSampler(DDPMSampler):
             if to_unit_range:
                 ims = (torch.clamp(ims, -1., 1.) + 1) / 2
             outs.append(ims)
+        check_device_errors()
         return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
 
     @torch.no_grad()
@@ -226,7 +265,16 @@ class GraphedStudent:
         sc.copy_(cond)
         sh.copy_(hint)
         g.replay()
-        return out.clone()
+        res = out.clone()
+        check_device_errors()
+        return res
+
+
+def check_device_errors():
+    """A bounded mbarrier wait that expired makes a tensor-core kernel drain and leave garbage (csrc/tc_common.cuh); the
+    latch is read (and cleared) at the end of every public sampling call so that corrupt samples never return rc = 0."""
+    if rt.lib().cnb_tc_error_flag() != 0:
+        raise rt.CnbError("a tcgen05 pipeline wait timed out on the device (hang guard): results are invalid")
 
 
 def shard_bounds(total, world, rank):
@@ -238,10 +286,15 @@ def shard_bounds(total, world, rank):
 
 @torch.no_grad()
 def sample_data_parallel(model, scheduler, shape, hint_fn, steps=None, seed=0, group=None, use_graph=True,
-                         gather=True, vae=None):
-    """One job over all ranks of `group`: rank r draws and denoises samples [lo, hi) and the final samples are
-    all-gathered once.  `hint_fn(lo, hi)` returns this shard's hint tensor on the local device.  With `vae` the
-    shard's final latents are decoded locally (LDM path) and the images are what is gathered."""
+                         gather=True, vae=None, sampler=None, x_T_fn=None):
+    """One job over all ranks of `group` (tools/sample_ddpm_controlnet.py:21-51 sharded over the GPUs of a box): rank r
+    draws (or receives) and denoises samples [lo, hi) of the global batch `shape[0]`, no collective inside the
+    timestep loop, and the final samples are all-gathered ONCE (NCCL over NVLink).
+    `hint_fn(lo, hi)` returns this shard's hint tensor on the local device (it may do the host -> device copy);
+    `x_T_fn(lo, hi)`, when given, supplies the shard's initial noise the same way (the reference draws x_T on the host,
+    :26-29); otherwise x_T is Philox noise keyed by the GLOBAL element index, independent of the number of ranks.
+    `sampler` re-uses a DDPMSampler / LDMSampler (and its captured step graph) across calls.  With `vae` the shard's
+    final latents are decoded locally (LDM path) and the images are what is gathered."""
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -251,9 +304,14 @@ def sample_data_parallel(model, scheduler, shape, hint_fn, steps=None, seed=0, g
     for d in shape[1:]:
         per *= d
     dev = torch.device("cuda", torch.cuda.current_device())
-    smp = (DDPMSampler(model, scheduler, seed=seed, use_graph=use_graph) if vae is None else
-           LDMSampler(model, scheduler, vae, seed=seed, use_graph=use_graph))
-    x_T = smp.draw_xT((hi - lo,) + tuple(shape[1:]), dev, elem_offset=lo * per)
+    smp = sampler
+    if smp is None:
+        smp = (DDPMSampler(model, scheduler, seed=seed, use_graph=use_graph) if vae is None else
+               LDMSampler(model, scheduler, vae, seed=seed, use_graph=use_graph))
+    if x_T_fn is not None:
+        x_T = x_T_fn(lo, hi)
+    else:
+        x_T = smp.draw_xT((hi - lo,) + tuple(shape[1:]), dev, elem_offset=lo * per)
     xt, x0 = smp.sample(x_T, hint_fn(lo, hi), steps=steps, elem_offset=lo * per)
     if vae is not None:
         xt = smp.decode(xt)

@@ -35,8 +35,9 @@ extern "C" {
 
 /* compute modes of the GEMM-class entry points */
 #define CNB_MODE_F32 0   /* CUDA-core FFMA, exact fp32 ("fp32 mode", 1e-4 gate)                      */
-#define CNB_MODE_TF32 1  /* tcgen05.mma kind::tf32, fp32 operands in smem, fp32 accumulate in TMEM  */
-#define CNB_MODE_BF16 2  /* tcgen05.mma kind::f16 (bf16 operands), fp32 accumulate in TMEM          */
+#define CNB_MODE_F16 1   /* tensor-core mode: tcgen05.mma kind::f16 on fp16 operands (fp16 activation stream), kind::tf32
+                          * where a tensor is still fp32; fp32 accumulate in TMEM, fp32 statistics ("f16 mode", 1e-2 gate).
+                          * There is no bf16 mode: bf16 operands miss the 1e-2 gate on the MNIST widths. */
 
 typedef void* cnb_stream_t; /* cudaStream_t */
 
@@ -96,14 +97,13 @@ typedef struct cnb_conv_params {
 
 int cnb_conv2d(const cnb_conv_params* p, cnb_stream_t stream);
 
-/* OIHW -> [O][KH*KW][I] (tap = ky*KW+kx).  round_tf32 != 0 rounds to nearest tf32 (for CNB_MODE_TF32). */
+/* OIHW -> [O][KH*KW][I] (tap = ky*KW+kx).  round_tf32 != 0 rounds to nearest tf32 (for CNB_MODE_F16). */
 int cnb_pack_conv_weight(const float* w_oihw, float* dst, int O, int I, int KH, int KW, int round_tf32,
                          cnb_stream_t stream);
 /* ConvTranspose2d weight (I, O, 4, 4), stride 2, pad 1 -> [4 phases (py*2+px)][O][4 taps (a*2+b)][I]
  * with the taps of SURVEY.md Appendix F: T(0) = {(ky=1,dy=0),(ky=3,dy=-1)}, T(1) = {(ky=0,dy=+1),(ky=2,dy=0)}. */
 int cnb_pack_convT_weight(const float* w_iohw, float* dst, int I, int O, int round_tf32, cnb_stream_t stream);
-/* fp32 -> bf16 / fp16 (round to nearest even) */
-int cnb_cast_bf16(const float* src, void* dst, long long n, cnb_stream_t stream);
+/* fp32 -> fp16 (round to nearest even) */
 int cnb_cast_f16(const float* src, void* dst, long long n, cnb_stream_t stream);
 
 /*

@@ -30,13 +30,13 @@ zs = [syn.det_noise(f"config1:z{k}", tuple(x.shape)) for k in range(50)]
 g = golden("config1_mnist_b16_50step")
 sched = sch.LinearNoiseScheduler(**syn.MNIST_DIFFUSION)
 xc, hc = x.cuda(), hint.cuda()
-for mode in ("fp32", "tf32"):
+for mode in ("fp32", "f16"):
     rt.set_mode(mode)
     xt, x0 = S.DDPMSampler(m, sched, use_graph=False).sample_eager(xc, hc, steps=50, zs=zs)
     print(f"[{mode}] final x0: PSNR {psnr(x0.cpu(), g['x0']):.1f} dB, max-abs {max_abs(x0.cpu(), g['x0']):.3e}, "
           f"rel-L2 {rel_l2(x0.cpu(), g['x0']):.3e}; x_t-1 rel-L2 {rel_l2(xt.cpu(), g['xt']):.3e}", flush=True)
 
-rt.set_mode("tf32")
+rt.set_mode("f16")
 smp = S.DDPMSampler(m, sched, seed=1, use_graph=True)
 xh, hh = x.pin_memory(), hint.pin_memory()
 out = torch.empty_like(x).pin_memory()

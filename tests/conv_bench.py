@@ -44,7 +44,7 @@ if what in ("conv", "all"):
     only = os.environ.get("CB_ONLY")
     if only:
         shapes = [shapes[int(i)] for i in only.split(",")]
-    variants = [("f16", rt.MODE_TF32, True), ("tf32", rt.MODE_TF32, False)]
+    variants = [("f16", rt.MODE_F16, True), ("tf32", rt.MODE_F16, False)]
     if os.environ.get("CB_VARIANT"):
         variants = [v for v in variants if v[0] == os.environ["CB_VARIANT"]]
     if os.environ.get("CB_FP32", "0") == "1":
@@ -71,7 +71,7 @@ if what in ("conv", "all"):
                   f"{by / ms / 1e6:8.1f} GB/s(min-traffic)", flush=True)
 
 if what in ("attn", "all"):
-    for mode in ((rt.MODE_TF32, rt.MODE_F32) if os.environ.get("CB_FP32", "0") == "1" else (rt.MODE_TF32,)):
+    for mode in ((rt.MODE_F16, rt.MODE_F32) if os.environ.get("CB_FP32", "0") == "1" else (rt.MODE_F16,)):
         ashapes = [(784, 64, 4), (784, 16, 4), (196, 128, 4), (196, 32, 4), (49, 256, 4), (49, 128, 4), (49, 64, 4),
                    (1024, 384, 16), (1024, 128, 16), (256, 512, 16), (64, 768, 16)]   # last four: CelebHQ LDM levels
         if os.environ.get("CB_ONLY"):

@@ -36,13 +36,13 @@ if os.environ.get("LDM_PARITY", "1") == "1":
     with torch.no_grad():
         want = O.controlnet_ldm_forward(sd, cfg, x, t, hint)
     print(f"oracle (CPU fp32, batch 1): {time.time() - t1:.1f} s", flush=True)
-    for mode in ("fp32", "tf32"):
+    for mode in ("fp32", "f16"):
         rt.set_mode(mode)
         with torch.no_grad():
             got = m(x.cuda(), t.cuda(), hint.cuda())
         print(f"mode {mode}: eps rel-L2 vs oracle = {rel_l2(got.cpu(), want):.3e}  flag={rt.lib().cnb_tc_error_flag()}", flush=True)
 
-rt.set_mode("tf32")
+rt.set_mode("f16")
 for B in [int(a) for a in sys.argv[1:]] or [16, 64]:
     x = torch.randn(B, 4, 32, 32, device="cuda")
     hint = (torch.rand(B, 1, 1024, 1024, device="cuda") < 0.05).float().expand(B, 3, 1024, 1024).contiguous()

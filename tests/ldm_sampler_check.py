@@ -15,7 +15,7 @@ from helpers import syn  # noqa: E402
 
 rt = importlib.import_module("controlnet-pytorch_b200.runtime")
 rt.lib()
-rt.set_mode("tf32")
+rt.set_mode("f16")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 CN = importlib.import_module("controlnet-pytorch_b200.models.controlnet_ldm").ControlNet

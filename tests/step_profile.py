@@ -17,7 +17,7 @@ S = importlib.import_module("controlnet-pytorch_b200.sampler")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 dev = torch.device("cuda", 0)
 rt.lib()
-rt.set_mode(os.environ.get("CNB_MODE", "tf32"))
+rt.set_mode(os.environ.get("CNB_MODE", "f16"))
 cfg, model, sched, hint_host = bench.build_problem(B, dev)
 hint = hint_host.to(dev)
 x = torch.randn(B, 1, 28, 28, device=dev)

@@ -15,7 +15,7 @@ from helpers import syn  # noqa: E402
 
 rt = importlib.import_module("controlnet-pytorch_b200.runtime")
 rt.lib()
-rt.set_mode("tf32")
+rt.set_mode("f16")
 
 
 def fill(m):

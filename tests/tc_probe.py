@@ -25,7 +25,7 @@ for (M, N, K) in [(128, 16, 32), (128, 64, 32), (128, 128, 32), (128, 64, 64), (
     ref = (a.double() @ w.double().t()).float()
     ad, wd = a.cuda(), w.cuda()
     out = torch.full((M, N), float("nan"), device="cuda")
-    rc = L.cnb_tc_gemm_selftest(ad.data_ptr(), wd.data_ptr(), out.data_ptr(), M, N, K, rt.MODE_TF32, 0)
+    rc = L.cnb_tc_gemm_selftest(ad.data_ptr(), wd.data_ptr(), out.data_ptr(), M, N, K, rt.MODE_F16, 0)
     flag = L.cnb_tc_error_flag()
     o = out.cpu()
     nan = int(torch.isnan(o).sum())

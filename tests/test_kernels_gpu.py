@@ -69,11 +69,11 @@ def _conv_ref(kind, x, w, b):
     raise ValueError(kind)
 
 
-@pytest.mark.parametrize("mode,tol", [("fp32", 2e-6), ("tf32", 2e-3)])
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-6), ("f16", 2e-3)])
 @pytest.mark.parametrize("kind,B,Cin,Cout,H,W", CONV_CASES)
 def test_conv(pk, kind, B, Cin, Cout, H, W, mode, tol):
     ops, rt = pk
-    m = {"fp32": rt.MODE_F32, "tf32": rt.MODE_TF32}[mode]
+    m = {"fp32": rt.MODE_F32, "f16": rt.MODE_F16}[mode]
     k = {"3x3": 3, "1x1": 1, "4x4s2": 4, "3x3s2": 3}[kind]
     x, w, b = rnd(B, Cin, H, W, seed=1), rnd(Cout, Cin, k, k, seed=2) / math.sqrt(Cin * k * k), rnd(Cout, seed=3)
     want = _conv_ref(kind, x, w, b)
@@ -86,7 +86,7 @@ def test_conv(pk, kind, B, Cin, Cout, H, W, mode, tol):
     got = ops.conv(nhwc(x).cuda(), wp, kind, Cout, bias=b.cuda(), temb=temb.cuda(), temb_ld=Cout,
                    temb_per_sample=True, residual=nhwc(res).cuda(), act=1, mode=m)
     assert rel_l2(nchw(got.cpu()), want_full) < tol
-    if m == rt.MODE_TF32:
+    if m == rt.MODE_F16:
         assert rt.lib().cnb_tc_error_flag() == 0
 
 
@@ -101,24 +101,24 @@ def test_conv_f16_operands(pk, kind, B, Cin, Cout, H, W):
     want = _conv_ref(kind, x, w, b) + res
     want_q = _conv_ref(kind, x.half().float(), w.half().float(), b) + res     # same operand rounding, exact math
     wp = ops.pack_conv_weight(w.cuda(), round_tf32=False)
-    got = ops.conv(nhwc(x).cuda().half(), wp, kind, Cout, bias=b.cuda(), residual=nhwc(res).cuda(), mode=rt.MODE_TF32,
+    got = ops.conv(nhwc(x).cuda().half(), wp, kind, Cout, bias=b.cuda(), residual=nhwc(res).cuda(), mode=rt.MODE_F16,
                    weight_lp=ops.cast_f16(wp))
     assert got.dtype == torch.float32
     assert rel_l2(nchw(got.cpu()), want_q) < 5e-6
     assert rel_l2(nchw(got.cpu()), want) < 1e-3
-    got16 = ops.conv(nhwc(x).cuda().half(), wp, kind, Cout, bias=b.cuda(), residual=nhwc(res).cuda(), mode=rt.MODE_TF32,
+    got16 = ops.conv(nhwc(x).cuda().half(), wp, kind, Cout, bias=b.cuda(), residual=nhwc(res).cuda(), mode=rt.MODE_F16,
                      weight_lp=ops.cast_f16(wp), out_f16=True)
     assert got16.dtype == torch.float16
     assert rel_l2(nchw(got16.float().cpu()), want_q) < 6e-4
     assert rt.lib().cnb_tc_error_flag() == 0
 
 
-@pytest.mark.parametrize("mode,tol", [("fp32", 2e-6), ("tf32", 2e-3)])
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-6), ("f16", 2e-3)])
 @pytest.mark.parametrize("B,C,H,W", [(2, 32, 7, 7), (1, 64, 14, 14), (3, 16, 5, 3)])
 def test_conv_transpose_into_concat(pk, B, C, H, W, mode, tol):
     """4 parity phases written into the first half of a 2C-channel concat buffer (UpBlock, unet_base.py:268-269)."""
     ops, rt = pk
-    m = {"fp32": rt.MODE_F32, "tf32": rt.MODE_TF32}[mode]
+    m = {"fp32": rt.MODE_F32, "f16": rt.MODE_F16}[mode]
     x, w, b = rnd(B, C, H, W, seed=1), rnd(C, C, 4, 4, seed=2) / math.sqrt(4 * C), rnd(C, seed=3)
     skip = rnd(B, C, 2 * H, 2 * W, seed=4)
     want = torch.cat([F.conv_transpose2d(x, w, b, stride=2, padding=1), skip], dim=1)
@@ -182,10 +182,10 @@ def test_groupnorm_large_samples(pk, B, C, G, H, W, silu):
 @pytest.mark.parametrize("B,L,E,heads", [(2, 784, 64, 4), (2, 784, 16, 4), (3, 196, 128, 4), (2, 49, 256, 4),
                                          (2, 196, 32, 4), (1, 1024, 384, 16), (2, 64, 768, 16), (2, 16, 512, 16),
                                          (1, 64, 512, 4), (1, 100, 384, 4), (1, 50, 768, 4), (2, 1, 64, 4), (1, 13, 32, 4)])
-@pytest.mark.parametrize("mode,tol", [("fp32", 3e-6), ("tf32", 2e-3)])
+@pytest.mark.parametrize("mode,tol", [("fp32", 3e-6), ("f16", 2e-3)])
 def test_attention(pk, B, L, E, heads, mode, tol):
     ops, rt = pk
-    m = {"fp32": rt.MODE_F32, "tf32": rt.MODE_TF32}[mode]
+    m = {"fp32": rt.MODE_F32, "f16": rt.MODE_F16}[mode]
     qkv = rnd(B, L, 3 * E, seed=1)
     d = E // heads
     q, k, v = [t.reshape(B, L, heads, d).transpose(1, 2) for t in qkv.split(E, dim=-1)]
@@ -263,7 +263,7 @@ def test_conv_k_concat_second_input(pk, B, C, Cx, Cout, H, W):
     p3, p1 = ops.pack_conv_weight(w3.cuda(), False), ops.pack_conv_weight(w1.cuda(), False)
     wcat = ops.cast_f16(torch.cat([p3.reshape(Cout, -1), p1.reshape(Cout, -1)], dim=1).contiguous())
     got = ops.conv(nhwc(h).cuda().half(), p3, "3x3", Cout, bias=b3.cuda(), temb=b1.cuda(), temb_ld=Cout,
-                   mode=rt.MODE_TF32, weight_lp=wcat, out_f16=True, x2=nhwc(x).cuda().half())
+                   mode=rt.MODE_F16, weight_lp=wcat, out_f16=True, x2=nhwc(x).cuda().half())
     assert got.dtype == torch.float16
     assert rel_l2(nchw(got.float().cpu()), want) < 6e-4
     assert rt.lib().cnb_tc_error_flag() == 0
@@ -274,7 +274,7 @@ def test_conv_out_reads_fp16(pk):
     ops, rt = pk
     x, w, b = rnd(3, 16, 9, 7, seed=1), rnd(1, 16, 3, 3, seed=2) / 12.0, rnd(1, seed=3)
     want = F.conv2d(x.half().float(), w, b, padding=1)
-    got = ops.conv(nhwc(x).cuda().half(), ops.pack_conv_weight(w.cuda(), False), "3x3", 1, bias=b.cuda(), mode=rt.MODE_TF32)
+    got = ops.conv(nhwc(x).cuda().half(), ops.pack_conv_weight(w.cuda(), False), "3x3", 1, bias=b.cuda(), mode=rt.MODE_F16)
     assert rel_l2(nchw(got.cpu()), want) < 2e-6
 
 
@@ -359,10 +359,14 @@ def test_layout_and_scale(pk):
 
 
 def test_no_cpu_fallback(pk):
+    """Every op rejects host tensors; the public model forward STAGES them to the device instead (models/_entry.py,
+    tests/test_models_gpu.py::test_host_tensors_are_staged_not_computed_on_the_host) - nothing computes on the host."""
     ops, rt = pk
     with pytest.raises(rt.CnbError):
         ops.groupnorm(torch.zeros(1, 2, 2, 16), torch.ones(16), torch.zeros(16), 8, True)
-    mod = importlib.import_module("controlnet-pytorch_b200.models.controlnet")
-    m = mod.ControlNet(syn.TINY_PARAMS)
     with pytest.raises(rt.CnbError):
-        m(torch.zeros(1, 1, 16, 16), torch.tensor([3]), torch.zeros(1, 3, 16, 16))
+        ops.conv(torch.zeros(1, 4, 4, 16), torch.zeros(16, 1, 16), "1x1", 16)
+    mod = importlib.import_module("controlnet-pytorch_b200.scheduler.linear_noise_scheduler")
+    s = mod.LinearNoiseScheduler(**syn.MNIST_DIFFUSION)
+    with pytest.raises(rt.CnbError):
+        s.sample_prev_timestep(torch.zeros(1, 1, 4, 4), torch.zeros(1, 1, 4, 4), torch.as_tensor(5))

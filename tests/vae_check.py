@@ -18,7 +18,7 @@ VAE = importlib.import_module("controlnet-pytorch_b200.models.vae").VAE
 m = VAE(3, syn.CELEBHQ_VAE_PARAMS)
 m.load_state_dict(syn.det_state_dict(m.state_dict(), 0))
 m = m.cuda().eval()
-rt.set_mode("tf32")
+rt.set_mode("f16")
 for B in [int(a) for a in sys.argv[1:]] or [16, 64]:
     z = torch.randn(B, 4, 32, 32, device="cuda")
     with torch.no_grad():
