@@ -51,9 +51,9 @@ int attention_tc(const float* qkv, float* out, int B, int L, int E, int heads, c
 bool attention_tc_supported(int E, int heads);
 int attention_f16(const void* qkv, void* out, int B, int L, int E, int heads, cudaStream_t st);
 bool attention_f16_supported(int E, int heads);
-int attention_tc05(const void* qkv, void* out, int B, int L, int E, int heads, cudaStream_t st);
-bool attention_tc05_supported(const void* qkv, const void* out, int B, int L, int E, int heads);
-bool attention_tc05_default();
+int attention_tmem(const void* qkv, void* out, int B, int L, int E, int heads, cudaStream_t st);
+bool attention_tmem_supported(const void* qkv, const void* out, int B, int L, int E, int heads);
+bool attention_tmem_default(int L);
 
 static int g_has_tc = -1;
 static int query_tc() {
@@ -155,18 +155,29 @@ extern "C" int cnb_attention_f16(const void* qkv, void* out, int B, int L, int E
     set_error("attention_f16: E=%d heads=%d (head dim %d) is not instantiated", E, heads, heads > 0 ? E / heads : 0);
     return CNB_ERR_UNSUPPORTED;
   }
-  // CNB_ATTN_TC05=1 routes long sequences at head dim 16 / 32 to the tcgen05 / TMEM kernel; the default is the
-  // register-resident mma.sync kernel, which is faster at these head dims
-  if (attention_tc05_default() && attention_tc05_supported(qkv, out, B, L, E, heads))
-    return attention_tc05(qkv, out, B, L, E, heads, (cudaStream_t)stream);
+  // default: the tcgen05 / TMEM kernel (S, P and O in tensor memory, csrc/attention_tmem.cu) for every head dim it
+  // instantiates; CNB_ATTN_TMEM=0 (or a sequence shorter than CNB_ATTN_TMEM_MINL) takes the register-resident mma.sync
+  // kernel, which also covers the head dims above 64
+  if (attention_tmem_default(L) && attention_tmem_supported(qkv, out, B, L, E, heads))
+    return attention_tmem(qkv, out, B, L, E, heads, (cudaStream_t)stream);
   return attention_f16(qkv, out, B, L, E, heads, (cudaStream_t)stream);
 }
 
-extern "C" int cnb_attention_tc05(const void* qkv, void* out, int B, int L, int E, int heads, cnb_stream_t stream) {
-  CNB_REQUIRE(qkv && out && B > 0 && L > 0 && E > 0, "attention_tc05: bad args");
-  if (!attention_tc05_supported(qkv, out, B, L, E, heads)) {
-    set_error("attention_tc05: needs head dim 16 or 32, L >= 96, 16-byte aligned fp16 rows (E=%d heads=%d L=%d)", E, heads, L);
+extern "C" int cnb_attention_tmem(const void* qkv, void* out, int B, int L, int E, int heads, cnb_stream_t stream) {
+  CNB_REQUIRE(qkv && out && B > 0 && L > 0 && E > 0, "attention_tmem: bad args");
+  if (!attention_tmem_supported(qkv, out, B, L, E, heads)) {
+    set_error("attention_tmem: needs head dim in {4, 8, 16, 24, 32, 48, 64} and 16-byte aligned fp16 rows (E=%d heads=%d L=%d)",
+              E, heads, L);
     return CNB_ERR_UNSUPPORTED;
   }
-  return attention_tc05(qkv, out, B, L, E, heads, (cudaStream_t)stream);
+  return attention_tmem(qkv, out, B, L, E, heads, (cudaStream_t)stream);
+}
+
+extern "C" int cnb_attention_mma(const void* qkv, void* out, int B, int L, int E, int heads, cnb_stream_t stream) {
+  CNB_REQUIRE(qkv && out && B > 0 && L > 0 && E > 0, "attention_mma: bad args");
+  if (!attention_f16_supported(E, heads)) {
+    set_error("attention_mma: E=%d heads=%d (head dim %d) is not instantiated", E, heads, heads > 0 ? E / heads : 0);
+    return CNB_ERR_UNSUPPORTED;
+  }
+  return attention_f16(qkv, out, B, L, E, heads, (cudaStream_t)stream);
 }

@@ -24,7 +24,7 @@
 namespace cnb {
 
 int conv_tma_error_flag();        // conv_tma.cu
-int attention_tc05_error_flag();  // attention_tc05.cu
+int attention_tmem_error_flag();  // attention_tmem.cu
 
 namespace tc {
 
@@ -361,7 +361,7 @@ extern "C" int cnb_tc_error_flag(void) {
     cnb::set_error("device error: %s", cudaGetErrorString(e));
     return CNB_ERR_CUDA;
   }
-  const int h1 = cnb::tc_read_clear_error(), h2 = cnb::conv_tma_error_flag() | cnb::attention_tc05_error_flag();
+  const int h1 = cnb::tc_read_clear_error(), h2 = cnb::conv_tma_error_flag() | cnb::attention_tmem_error_flag();
   if (h1 < 0 || h2 < 0) {
     cnb::set_error("cudaMemcpyFromSymbol failed while reading the tcgen05 hang-guard flag");
     return CNB_ERR_CUDA;

@@ -125,14 +125,15 @@ def cast_f16(x):
     return y
 
 
-def attention(qkv, heads, mode=None, tc05=False):
-    """qkv: (B, H, W, 3E) -> (B, H, W, E).  tc05=True forces the tcgen05 / TMEM kernel (fp16, head dim 16 / 32)."""
+def attention(qkv, heads, mode=None, kernel=None):
+    """qkv: (B, H, W, 3E) -> (B, H, W, E).  kernel: None = library default, "tmem" forces the tcgen05 / TMEM kernel,
+    "mma" the mma.sync kernel (fp16 tensors only)."""
     rt.require_cuda(qkv)
     B, H, W, E3 = qkv.shape
     E = E3 // 3
     if qkv.dtype == torch.float16:
         out = torch.empty((B, H, W, E), device=qkv.device, dtype=torch.float16)
-        fn = rt.lib().cnb_attention_tc05 if tc05 else rt.lib().cnb_attention_f16
+        fn = {None: rt.lib().cnb_attention_f16, "tmem": rt.lib().cnb_attention_tmem, "mma": rt.lib().cnb_attention_mma}[kernel]
         rt.check(fn(qkv.data_ptr(), out.data_ptr(), B, H * W, E, heads, rt.stream()))
         return out
     out = torch.empty((B, H, W, E), device=qkv.device, dtype=torch.float32)

@@ -53,7 +53,8 @@ _SIGS = {
                                  c_int, c_int, c_void_p, ctypes.c_size_t, c_void_p]),
     "cnb_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "cnb_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "cnb_attention_tc05": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "cnb_attention_tmem": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "cnb_attention_mma": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "cnb_linear_small": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p]),
     "cnb_time_embedding": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
@@ -160,6 +161,13 @@ def get_mode():
 def mode_name(m=None):
     m = get_mode() if m is None else m
     return {MODE_F32: "fp32", MODE_F16: "f16"}[m]
+
+
+def attention_kernel_name():
+    """Name of the kernel cnb_attention_f16 dispatches to by default (bench.py's roofline label)."""
+    if os.environ.get("CNB_ATTN_TMEM", "1") != "0":
+        return "attention_tmem_kernel (tcgen05.mma SS + TS, S/P/O in TMEM, TMA)"
+    return "attention_f16_kernel (mma.sync m16n8k16)"
 
 
 def launch_count():

@@ -118,7 +118,7 @@ class DDPMSampler:
             rt.check(L.cnb_bump_index(self.step_idx.data_ptr(), 1, rt.stream()))
 
         from .models import _controlnet_common as _cc
-        _cc.set_branch_parallel(False if nsplit > 1 else None)
+        _cc.set_branch_parallel(False if (nsplit > 1 and os.environ.get("CNB_SPLIT_KEEP_BRANCH", "0") != "1") else None)
         try:
             if nsplit > 1:
                 # cold caches: ONE unsplit forward on a single stream packs every weight / builds the t-embedding table

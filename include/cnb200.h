@@ -130,12 +130,17 @@ int cnb_groupnorm_ws(const void* x, void* y, const float* gamma, const float* be
  */
 int cnb_attention(const float* qkv, float* out, int B, int L, int E, int heads, int mode, cnb_stream_t stream);
 /* Same contraction on fp16 operands: qkv [B, L, 3E] fp16 (as the in_proj convolution emits it with out_dtype 1),
- * out [B, L, E] fp16 (the A operand of the out_proj convolution); fp32 softmax statistics and accumulators. */
+ * out [B, L, E] fp16 (the A operand of the out_proj convolution); fp32 softmax statistics and accumulators.
+ * Dispatches to cnb_attention_tmem for every head dim that kernel instantiates (CNB_ATTN_TMEM=0: never), else to
+ * cnb_attention_mma. */
 int cnb_attention_f16(const void* qkv, void* out, int B, int L, int E, int heads, cnb_stream_t stream);
-/* Same contract as cnb_attention_f16 on the tcgen05 / TMEM flash-attention kernel (head dim 16 or 32, L >= 96):
- * S = Q K^T and O += P V run as tcgen05.mma tiles fed by TMA, accumulators in tensor memory, split-K online softmax
- * with lazy rescale.  cnb_attention_f16 dispatches here when CNB_ATTN_TC05=1. */
-int cnb_attention_tc05(const void* qkv, void* out, int B, int L, int E, int heads, cnb_stream_t stream);
+/* The tcgen05 / TMEM flash-attention kernel (csrc/attention_tmem.cu; head dim 4, 8, 16, 24, 32, 48 or 64):
+ * S = Q K^T as tcgen05.mma tiles fed by TMA, S / P / O resident in tensor memory (P is the A operand of the second MMA
+ * straight from TMEM), thread-per-row online softmax with lazy rescale, denominator accumulated by the tensor core. */
+int cnb_attention_tmem(const void* qkv, void* out, int B, int L, int E, int heads, cnb_stream_t stream);
+/* The register-resident mma.sync (m16n8k16) flash-attention kernel (csrc/attention_f16.cu): head dims the TMEM kernel
+ * does not instantiate (96, 128, 192: CelebHQ-latent students) and the comparison arm of the kernel tests. */
+int cnb_attention_mma(const void* qkv, void* out, int B, int L, int E, int heads, cnb_stream_t stream);
 
 /* y[r, n] = post( sum_k pre(x[r, k]) * w[n, k] + b[n] ), pre/post = SiLU if the flag is set.  x is [R, K]
  * contiguous, y has leading dimension ldy.   Replaces Unet.t_proj (unet_base.py:313-317), the per-block

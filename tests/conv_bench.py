@@ -82,7 +82,7 @@ if what in ("attn", "all"):
             qkv = torch.randn(Bq, side, side, 3 * E, device="cuda")
             if os.environ.get("CB_ATTN_F16", "1") == "1" and mode != rt.MODE_F32:
                 qkv = qkv.half()
-            ms = timeit(lambda: ops.attention(qkv, heads, mode=mode, tc05=os.environ.get('CB_TC05', '0') == '1'))
+            ms = timeit(lambda: ops.attention(qkv, heads, mode=mode, kernel=os.environ.get('CB_ATTN_KERNEL') or None))
             fl = 4.0 * Bq * L * L * E
             print(f"attn[{rt.mode_name(mode)}] L={L} E={E} d={E // heads}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:8.2f} TFLOP/s  "
                   f"{Bq * heads * L * L / ms / 1e6:8.2f} Gscore/s", flush=True)

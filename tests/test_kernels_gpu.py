@@ -179,58 +179,69 @@ def test_groupnorm_large_samples(pk, B, C, G, H, W, silu):
         assert torch.equal(one, ops.groupnorm(xc, g.cuda(), b.cuda(), G, silu, out_f16=True)[:1])
 
 
-@pytest.mark.parametrize("B,L,E,heads", [(2, 784, 64, 4), (2, 784, 16, 4), (3, 196, 128, 4), (2, 49, 256, 4),
-                                         (2, 196, 32, 4), (1, 1024, 384, 16), (2, 64, 768, 16), (2, 16, 512, 16),
-                                         (1, 64, 512, 4), (1, 100, 384, 4), (1, 50, 768, 4), (2, 1, 64, 4), (1, 13, 32, 4)])
-@pytest.mark.parametrize("mode,tol", [("fp32", 3e-6), ("f16", 2e-3)])
-def test_attention(pk, B, L, E, heads, mode, tol):
-    ops, rt = pk
-    m = {"fp32": rt.MODE_F32, "f16": rt.MODE_F16}[mode]
-    qkv = rnd(B, L, 3 * E, seed=1)
+ATTN_SHAPES = [(2, 784, 64, 4), (2, 784, 16, 4), (3, 196, 128, 4), (2, 49, 256, 4),
+               (2, 196, 32, 4), (1, 1024, 384, 16), (2, 64, 768, 16), (2, 16, 512, 16),
+               (1, 64, 512, 4), (1, 100, 384, 4), (1, 50, 768, 4), (2, 1, 64, 4), (1, 13, 32, 4),
+               (2, 1024, 128, 16), (3, 130, 64, 4)]
+
+
+def _attn_want(qkv, B, L, E, heads):
     d = E // heads
-    q, k, v = [t.reshape(B, L, heads, d).transpose(1, 2) for t in qkv.split(E, dim=-1)]
-    want = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), -1) @ v).transpose(1, 2).reshape(B, L, E)
-    got = ops.attention(qkv.reshape(B, L, 1, 3 * E).cuda(), heads, mode=m)
-    assert rel_l2(got.cpu().reshape(B, L, E), want) < tol
+    q, k, v = [t.float().reshape(B, L, heads, d).transpose(1, 2) for t in qkv.split(E, dim=-1)]
+    return (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), -1) @ v).transpose(1, 2).reshape(B, L, E)
 
 
-@pytest.mark.parametrize("B,L,E,heads", [(2, 784, 64, 4), (2, 784, 16, 4), (3, 196, 128, 4), (2, 49, 256, 4),
-                                         (2, 196, 32, 4), (1, 1024, 384, 16), (2, 64, 768, 16), (2, 16, 512, 16),
-                                         (1, 64, 512, 4), (1, 100, 384, 4), (1, 50, 768, 4), (2, 1, 64, 4), (1, 13, 32, 4),
-                                         (2, 1024, 128, 16), (3, 130, 64, 4)])
-def test_attention_f16(pk, B, L, E, heads):
-    """fp16-operand flash attention (mma.sync m16n8k16 + ldmatrix) against exact softmax attention on the same
-    fp16-rounded q|k|v; tolerance = fp16 rounding of P and of the output."""
+@pytest.mark.parametrize("B,L,E,heads", ATTN_SHAPES)
+@pytest.mark.parametrize("kernel", [None, "mma"])
+def test_attention_f16(pk, B, L, E, heads, kernel):
+    """fp16-operand flash attention against exact softmax attention on the same fp16-rounded q|k|v; tolerance = fp16
+    rounding of P and of the output.  kernel=None is the library's routing (tcgen05 / TMEM kernel where it is
+    instantiated, the mma.sync kernel for head dims above 64); "mma" forces the mma.sync kernel."""
     ops, rt = pk
     qkv = rnd(B, L, 3 * E, seed=1).half()
-    d = E // heads
-    q, k, v = [t.float().reshape(B, L, heads, d).transpose(1, 2) for t in qkv.split(E, dim=-1)]
-    want = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), -1) @ v).transpose(1, 2).reshape(B, L, E)
-    got = ops.attention(qkv.reshape(B, L, 1, 3 * E).cuda(), heads)
-    assert got.dtype == torch.float16
-    assert rel_l2(got.float().cpu().reshape(B, L, E), want) < 1.5e-3
-
-
-@pytest.mark.parametrize("B,L,E,heads", [(2, 784, 64, 4), (3, 196, 128, 4), (2, 1024, 128, 8), (3, 130, 64, 4), (1, 96, 64, 4),
-                                         (2, 128, 32, 2), (1, 129, 64, 2), (5, 257, 256, 16), (2, 1024, 512, 16)])
-def test_attention_tc05(pk, B, L, E, heads):
-    """tcgen05 / TMEM flash attention (S and P V as tcgen05.mma tiles, split-K online softmax with lazy rescale, V
-    transposed in smem, denominators on the tensor core) against exact softmax attention on the same fp16 q|k|v."""
-    ops, rt = pk
-    qkv = rnd(B, L, 3 * E, seed=5).half()
-    d = E // heads
-    q, k, v = [t.float().reshape(B, L, heads, d).transpose(1, 2) for t in qkv.split(E, dim=-1)]
-    want = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), -1) @ v).transpose(1, 2).reshape(B, L, E)
-    got = ops.attention(qkv.reshape(B, L, 1, 3 * E).cuda(), heads, tc05=True)
+    want = _attn_want(qkv, B, L, E, heads)
+    got = ops.attention(qkv.reshape(B, L, 1, 3 * E).cuda(), heads, kernel=kernel)
     assert got.dtype == torch.float16
     assert rel_l2(got.float().cpu().reshape(B, L, E), want) < 1.5e-3
     assert rt.lib().cnb_tc_error_flag() == 0
 
 
+@pytest.mark.parametrize("B,L,E,heads", [
+    (2, 784, 64, 4), (2, 784, 16, 4), (2, 196, 32, 4), (3, 196, 128, 4), (2, 49, 256, 4), (2, 49, 128, 4), (2, 49, 64, 4),   # MNIST
+    (1, 1024, 128, 4), (1, 256, 256, 4), (1, 1024, 16, 4), (1, 256, 64, 4), (2, 64, 256, 4),                                # CIFAR
+    (1, 1024, 384, 16), (1, 256, 512, 16), (2, 64, 768, 16), (2, 16, 512, 16), (1, 1024, 128, 16), (1, 256, 256, 16),      # CelebHQ
+    (3, 130, 64, 4), (1, 96, 64, 4), (2, 128, 32, 2), (1, 129, 64, 2), (5, 257, 256, 16), (2, 1, 64, 4), (1, 13, 32, 4),
+    (1, 113, 16, 4), (2, 225, 64, 4), (1, 897, 32, 4), (130, 49, 64, 4)])
+def test_attention_tmem(pk, B, L, E, heads):
+    """tcgen05 / TMEM flash attention (csrc/attention_tmem.cu: S = Q K^T from smem operands, P written over S in tensor
+    memory and consumed from there by the second MMA, thread-per-row online softmax with lazy rescale, V transposed in
+    smem, denominators on the tensor core) against exact softmax attention on the same fp16 q|k|v: every (L, head dim)
+    of the shipped configs, ragged tails on both the query and the key side, head dims that are loaded as part of a wider
+    channel group (4, 8, 24, 48)."""
+    ops, rt = pk
+    qkv = rnd(B, L, 3 * E, seed=5).half()
+    want = _attn_want(qkv, B, L, E, heads)
+    got = ops.attention(qkv.reshape(B, L, 1, 3 * E).cuda(), heads, kernel="tmem")
+    assert got.dtype == torch.float16
+    assert torch.isfinite(got).all()
+    assert rel_l2(got.float().cpu().reshape(B, L, E), want) < 1.5e-3
+    assert rt.lib().cnb_tc_error_flag() == 0
+
+
+def test_attention_tmem_is_batch_invariant(pk):
+    """rows of a large batch equal the same samples run alone (the data-parallel shards must reproduce the full job)."""
+    ops, rt = pk
+    B, L, E, heads = 64, 784, 64, 4
+    qkv = rnd(B, L, 3 * E, seed=9).half().reshape(B, L, 1, 3 * E).cuda()
+    full = ops.attention(qkv, heads, kernel="tmem")
+    part = ops.attention(qkv[5:7].contiguous(), heads, kernel="tmem")
+    assert torch.equal(full[5:7], part)
+
+
 @pytest.mark.parametrize("B,L,E,heads", [(2, 784, 64, 4), (2, 300, 128, 4), (1, 1024, 256, 16), (2, 97, 64, 4)])
 @pytest.mark.parametrize("gain", [4.0, 12.0])
-@pytest.mark.parametrize("tc05", [False, True])
-def test_attention_f16_growing_scores(pk, B, L, E, heads, gain, tc05):
+@pytest.mark.parametrize("kernel", ["mma", "tmem"])
+def test_attention_f16_growing_scores(pk, B, L, E, heads, gain, kernel):
     """Scores whose row maximum keeps growing along the key axis (keys scaled by a ramp): the running maximum of an
     online softmax has to move many times, which exercises the lazy O-rescale path of the tcgen05 kernel (reference
     maximum only moves past a 2^8 headroom) and the peaked-softmax regime (P underflow of the early keys)."""
@@ -244,7 +255,7 @@ def test_attention_f16_growing_scores(pk, B, L, E, heads, gain, tc05):
     qkv = torch.cat([q, k, v], dim=-1).half()
     q, k, v = [t.float().reshape(B, L, heads, d).transpose(1, 2) for t in qkv.split(E, dim=-1)]
     want = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), -1) @ v).transpose(1, 2).reshape(B, L, E)
-    got = ops.attention(qkv.reshape(B, L, 1, 3 * E).cuda(), heads, tc05=tc05)
+    got = ops.attention(qkv.reshape(B, L, 1, 3 * E).cuda(), heads, kernel=kernel)
     assert torch.isfinite(got).all()
     assert rel_l2(got.float().cpu().reshape(B, L, E), want) < 2e-3
     assert rt.lib().cnb_tc_error_flag() == 0
