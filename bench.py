@@ -214,7 +214,10 @@ def make_roofline(fams, step_ms, batch):
     n = sh["launches"]
     sec = sh["ms"] * 1e-3 / n                      # average launch duration
     rt = importlib.import_module("controlnet-pytorch_b200.runtime")
-    attn_name = rt.attention_kernel_name() if hasattr(rt, "attention_kernel_name") else "attention kernel"
+    attn_name = "attention kernel"
+    if dom == "attention":                                  # shape label: "L=784 E=64 heads=4"
+        kv = dict(t.split("=") for t in shape.split())
+        attn_name = rt.attention_kernel_name(int(kv["L"]), int(kv["E"]) // int(kv["heads"]))
     kernel_names = {"conv_tc": "conv_tma_kernel (tcgen05 + TMA)", "conv_small": "conv_small_*_kernel",
                     "groupnorm": "groupnorm_*_kernel", "attention": attn_name, "sched_step": "sched_step_kernel"}
     if dom in ("conv_tc", "attention"):

@@ -53,7 +53,7 @@ int attention_f16(const void* qkv, void* out, int B, int L, int E, int heads, cu
 bool attention_f16_supported(int E, int heads);
 int attention_tmem(const void* qkv, void* out, int B, int L, int E, int heads, cudaStream_t st);
 bool attention_tmem_supported(const void* qkv, const void* out, int B, int L, int E, int heads);
-bool attention_tmem_default(int L);
+bool attention_tmem_default(int L, int d);
 
 static int g_has_tc = -1;
 static int query_tc() {
@@ -155,10 +155,9 @@ extern "C" int cnb_attention_f16(const void* qkv, void* out, int B, int L, int E
     set_error("attention_f16: E=%d heads=%d (head dim %d) is not instantiated", E, heads, heads > 0 ? E / heads : 0);
     return CNB_ERR_UNSUPPORTED;
   }
-  // default: the tcgen05 / TMEM kernel (S, P and O in tensor memory, csrc/attention_tmem.cu) for every head dim it
-  // instantiates; CNB_ATTN_TMEM=0 (or a sequence shorter than CNB_ATTN_TMEM_MINL) takes the register-resident mma.sync
-  // kernel, which also covers the head dims above 64
-  if (attention_tmem_default(L) && attention_tmem_supported(qkv, out, B, L, E, heads))
+  // the tcgen05 / TMEM kernel (S, P and O in tensor memory, csrc/attention_tmem.cu) where it measured faster (head dim
+  // >= 24, >= 128 tokens: the CIFAR and CelebHQ-latent levels), the register-resident mma.sync kernel elsewhere
+  if (heads > 0 && attention_tmem_default(L, E / heads) && attention_tmem_supported(qkv, out, B, L, E, heads))
     return attention_tmem(qkv, out, B, L, E, heads, (cudaStream_t)stream);
   return attention_f16(qkv, out, B, L, E, heads, (cudaStream_t)stream);
 }

@@ -74,11 +74,14 @@ if what in ("attn", "all"):
     for mode in ((rt.MODE_F16, rt.MODE_F32) if os.environ.get("CB_FP32", "0") == "1" else (rt.MODE_F16,)):
         ashapes = [(784, 64, 4), (784, 16, 4), (196, 128, 4), (196, 32, 4), (49, 256, 4), (49, 128, 4), (49, 64, 4),
                    (1024, 384, 16), (1024, 128, 16), (256, 512, 16), (64, 768, 16)]   # last four: CelebHQ LDM levels
+        if os.environ.get("CB_SHAPES"):                        # "L,E,heads[,batch];..." (batch defaults to CB_BATCH)
+            ashapes = [tuple(int(v) for v in t.split(",")) for t in os.environ["CB_SHAPES"].split(";")]
         if os.environ.get("CB_ONLY"):
             ashapes = [ashapes[int(i)] for i in os.environ["CB_ONLY"].split(",")]
-        for L, E, heads in ashapes:
+        for shp in ashapes:
+            L, E, heads = shp[:3]
             side = int(math.isqrt(L))
-            Bq = B_LDM if heads == 16 else B
+            Bq = shp[3] if len(shp) > 3 else (B_LDM if heads == 16 else B)
             qkv = torch.randn(Bq, side, side, 3 * E, device="cuda")
             if os.environ.get("CB_ATTN_F16", "1") == "1" and mode != rt.MODE_F32:
                 qkv = qkv.half()
