@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -41,6 +42,15 @@ void count_launch(int n = 1);
   } while (0)
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+// fp16 activation stream, overflow policy: SATURATE.  An activation beyond the fp16 range (65504) is stored as +-65504,
+// never as inf - an inf in the residual stream turns the next GroupNorm's statistics into NaN for the whole sample, a
+// saturated value only distorts its own group (tests/test_models_gpu.py::test_f16_mode_activation_range).  Two FMNMX per
+// pair on a store-bound epilogue: below measurement noise on the step.
+__device__ __forceinline__ __half2 h2_sat(float x, float y) {
+  return __floats2half2_rn(fminf(fmaxf(x, -65504.f), 65504.f), fminf(fmaxf(y, -65504.f), 65504.f));
+}
+
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -90,7 +90,7 @@ conv_small_cin_kernel(const __grid_constant__ SmallArgs a) {
     }
     if (p.act == 1) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
     if (p.out_dtype == 1) {
-      const __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
+      const __half2 lo = h2_sat(o.x, o.y), hi = h2_sat(o.z, o.w);
       *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + pix * p.ldo + p.out_coff + n) =
           make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
     } else {

@@ -228,15 +228,27 @@ int conv2d_tma(const cnb_conv_params* p, cudaStream_t st) {
   // ---- packed weights [Cout][K] -> tile {kc, BN}
   int bn = pick_bn(p->Cout);
   if (!halo) {
-    // latency regime (small batch): fewer tiles than a quarter of the SMs means a handful of CTAs stream all the weights of the
-    // layer; narrower N tiles spread them over more SMs (the K order, hence the result, does not change)
+    // Few tiles (small per-GPU batch, the strong-scaling regime): each CTA of an im2col layer streams the WHOLE weight matrix
+    // and its own A tile through one SM's L2 port (~64 B/clk: measured 24 us for 3x3 256+256->256 @7x7 at batch 128, 49
+    // CTAs on 49 SMs, 2 MB each, against 10 us of tensor time).  Narrower N tiles spread the weights over more SMs - the K
+    // order, hence the result, does not change.  Enter when the layer has fewer CTAs than SMs / ENTER, narrow until it has
+    // at least SMs / STOP (CNB_CONV_NSPLIT_ENTER / _STOP; measured defaults, profiles/r02_conv_nsplit.md).
+    static int ns_enter = -1, ns_stop = 2;
+    if (ns_enter < 0) {
+      const char* e = getenv("CNB_CONV_NSPLIT_ENTER");
+      ns_enter = e ? atoi(e) : 2;
+      const char* s2 = getenv("CNB_CONV_NSPLIT_STOP");
+      ns_stop = s2 ? atoi(s2) : 2;
+      if (ns_enter < 1) ns_enter = 1;
+      if (ns_stop < 1) ns_stop = 1;
+    }
     const int tiles_m = ceil_div((long long)p->B * p->OH * p->OW, BM);
-    if (tiles_m * (p->Cout / bn) * 4 <= g_num_sms) {
+    if (tiles_m * (p->Cout / bn) * ns_enter <= g_num_sms) {
       static const int cand[] = {128, 96, 64, 48, 32};
       for (int c : cand) {
         if (c >= bn || p->Cout % c) continue;
         bn = c;
-        if (tiles_m * (p->Cout / bn) * 2 >= g_num_sms) break;
+        if (tiles_m * (p->Cout / bn) * ns_stop >= g_num_sms) break;
       }
     }
   }

@@ -440,7 +440,7 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
               float4 o = *reinterpret_cast<const float4*>(slab + (size_t)(i * RPI + sub_r) * SSTR + sub_c);
               o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
               if (resh) { o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w; }
-              const __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
+              const __half2 lo = h2_sat(o.x, o.y), hi = h2_sat(o.z, o.w);
               *reinterpret_cast<uint2*>(outh + (size_t)rp * ldo + a.out_coff + n) =
                   make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
             }
@@ -460,7 +460,7 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
               o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
               if (EPI == 1 || EPI == 4) { o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w; }
               if (EPI == 2 || EPI == 4) {
-                const __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
+                const __half2 lo = h2_sat(o.x, o.y), hi = h2_sat(o.z, o.w);
                 *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(a.out) + o_off + (size_t)i * RPI * ldo) =
                     make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
               } else {
@@ -491,7 +491,7 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
               }
               if (a.act == 1) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
               if (a.out_f16) {
-                const __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
+                const __half2 lo = h2_sat(o.x, o.y), hi = h2_sat(o.z, o.w);
                 *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(a.out) + rp * ldo + a.out_coff + n) =
                     make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
               } else {

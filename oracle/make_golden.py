@@ -143,6 +143,49 @@ def make_vae():
 
 
 @torch.no_grad()
+def make_fullsize():
+    """Full-size BASELINE configs at batch 1: the 190 M-parameter CelebHQ LDM ControlNet eps
+    (config/celebhq.yaml ldm_params, hint 3 x 1024 x 1024, down_sample_factor 32), the CelebHQ-latent consistency student
+    (dict(ldm_params, im_channels=4, im_size=32)), and the multi-step generate() of the consistency
+    wrapper (consistency_controlnet_distilled.py:390-409) with its noise draws injected."""
+    cfg = syn.CELEBHQ_LDM_PARAMS
+    m = fill(RefControlNetLDM(4, cfg, down_sample_factor=32))
+    x, hint = inputs("celebhq_ldm", 1, 4, 32, hint_size=1024, p=0.05)
+    rec = {f"eps_{t}": m(x, torch.as_tensor(t).unsqueeze(0), hint).numpy() for t in (500, 3)}
+    np.savez_compressed(os.path.join(OUT, "controlnet_celebhq_ldm.npz"), **rec)
+    print("celebhq ldm", {k: (v.shape, float(np.abs(v).max())) for k, v in rec.items()})
+    del m
+    lat = dict(cfg, im_channels=4, im_size=32)
+    m = fill(RefCons(lat))
+    x, hint = inputs("cons_celebhq_latent", 1, 4, 32)
+    rec = {"x0_max": m(x, torch.full((1,), 80.0), hint).numpy(), "x0_mid": m(x, torch.full((1,), 1.7), hint).numpy()}
+    np.savez_compressed(os.path.join(OUT, "consistency_celebhq_latent.npz"), **rec)
+    print("celebhq-latent student", {k: v.shape for k, v in rec.items()})
+    del m
+    # multi-step generate: x_T and the re-noising draws come from torch.randn / randn_like (:383, :398) - injected
+    from models.consistency_controlnet_distilled import ConsistencyControlNetDistilled as RefConsD
+    import models.consistency_controlnet_distilled as ref_cd_mod
+    cfg = syn.TINY_PARAMS
+    w = RefConsD(cfg).eval()
+    w.student.load_state_dict(syn.det_state_dict(w.student.state_dict(), 0))
+    hint = syn.det_hint(2, 16)
+    shape = (2, 1, 16, 16)
+    rec = {}
+    for steps in (1, 4):
+        draws = [syn.det_noise(f"gen{steps}:n{k}", shape) for k in range(steps)]
+        orig_randn, orig_like = ref_cd_mod.torch.randn, ref_cd_mod.torch.randn_like
+        ref_cd_mod.torch.randn = lambda *a, **k: draws.pop(0)
+        ref_cd_mod.torch.randn_like = lambda *a, **k: draws.pop(0)
+        try:
+            rec[f"gen_{steps}"] = w.generate(hint, shape, num_steps=steps).numpy()
+        finally:
+            ref_cd_mod.torch.randn, ref_cd_mod.torch.randn_like = orig_randn, orig_like
+        assert not draws
+    np.savez_compressed(os.path.join(OUT, "consistency_generate_tiny.npz"), **rec)
+    print("generate", {k: (v.shape, float(np.abs(v).max())) for k, v in rec.items()})
+
+
+@torch.no_grad()
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -152,6 +195,8 @@ def main():
         return make_teachers()
     if "--only-config1" in sys.argv:
         return make_config1()
+    if "--only-fullsize" in sys.argv:
+        return make_fullsize()
 
     # ---- DDPM ControlNet: tiny / mnist / cifar
     for name, cfg, B, ts in (("tiny", syn.TINY_PARAMS, 2, (999, 37, 0)),
@@ -244,6 +289,7 @@ def main():
     make_vae()
     make_teachers()
     make_config1()
+    make_fullsize()
     print("done ->", OUT)
 
 
