@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libcnb200.so")
 STAMP = os.path.join(HERE, ".libcnb200.stamp")
-SOURCES = ["api.cu", "conv_f32.cu", "conv_small.cu", "conv_tc.cu", "conv_tma.cu", "conv_tma_f16.cu", "conv_tma_tf32.cu", "groupnorm.cu", "groupnorm_big.cu", "attention_f32.cu", "attention_tc.cu", "attention_f16.cu", "attention_tmem.cu", "elementwise.cu"]
+SOURCES = ["api.cu", "conv_f32.cu", "conv_small.cu", "conv_tma.cu", "conv_tma_f16.cu", "conv_tma_tf32.cu", "groupnorm.cu", "groupnorm_big.cu", "attention_f32.cu", "attention_f16.cu", "attention_tmem.cu", "elementwise.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math", "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-shared"]
 # --use_fast_math only affects the plain operators; every bit-exactness-critical expression in elementwise.cu

@@ -34,8 +34,6 @@ bool pdl_enabled(long long work) {
 }
 
 int conv2d_f32(const cnb_conv_params* p, cudaStream_t st);
-int conv2d_tc(const cnb_conv_params* p, cudaStream_t st);
-bool conv2d_tc_supported(const cnb_conv_params* p);
 int conv2d_small(const cnb_conv_params* p, cudaStream_t st);
 bool conv2d_small_supported(const cnb_conv_params* p);
 int conv2d_tma(const cnb_conv_params* p, cudaStream_t st);
@@ -47,8 +45,6 @@ int groupnorm_big(const void* x, void* y, const float* gamma, const float* beta,
 int groupnorm(const void* x, void* y, const float* gamma, const float* beta, int B, int HW, int C, int G,
               float eps, int silu, int in_f16, int out_f16, cudaStream_t st);
 int attention_f32(const float* qkv, float* out, int B, int L, int E, int heads, cudaStream_t st);
-int attention_tc(const float* qkv, float* out, int B, int L, int E, int heads, cudaStream_t st);
-bool attention_tc_supported(int E, int heads);
 int attention_f16(const void* qkv, void* out, int B, int L, int E, int heads, cudaStream_t st);
 bool attention_f16_supported(int E, int heads);
 int attention_tmem(const void* qkv, void* out, int B, int L, int E, int heads, cudaStream_t st);
@@ -110,7 +106,6 @@ extern "C" int cnb_conv2d(const cnb_conv_params* p, cnb_stream_t stream) {
   if (small_on && (p->Cin <= 4 || p->Cout <= 4) && conv2d_small_supported(p)) return conv2d_small(p, st);
   if (p->mode == CNB_MODE_F16) {
     if (conv2d_tma_supported(p)) return conv2d_tma(p, st);     // TMA-im2col fed persistent tcgen05 kernel
-    if (conv2d_tc_supported(p)) return conv2d_tc(p, st);       // cp.async-gather tcgen05 kernel (narrow Cin)
   } else if (p->mode != CNB_MODE_F32) {
     set_error("conv2d: unknown mode %d", p->mode);
     return CNB_ERR_BAD_ARG;
@@ -144,9 +139,8 @@ extern "C" int cnb_groupnorm(const void* x, void* y, const float* gamma, const f
 extern "C" int cnb_attention(const float* qkv, float* out, int B, int L, int E, int heads, int mode,
                              cnb_stream_t stream) {
   CNB_REQUIRE(qkv && out && B > 0 && L > 0 && E > 0, "attention: bad args");
-  if (mode != CNB_MODE_F32 && attention_tc_supported(E, heads))
-    return attention_tc(qkv, out, B, L, E, heads, (cudaStream_t)stream);
-  return attention_f32(qkv, out, B, L, E, heads, (cudaStream_t)stream);   // exact fp32 core (and odd head dims)
+  (void)mode;   // fp32 q|k|v always take the exact fp32 core (the tensor-core modes keep q|k|v in fp16: cnb_attention_f16)
+  return attention_f32(qkv, out, B, L, E, heads, (cudaStream_t)stream);
 }
 
 extern "C" int cnb_attention_f16(const void* qkv, void* out, int B, int L, int E, int heads, cnb_stream_t stream) {
@@ -179,4 +173,23 @@ extern "C" int cnb_attention_mma(const void* qkv, void* out, int B, int L, int E
     return CNB_ERR_UNSUPPORTED;
   }
   return attention_f16(qkv, out, B, L, E, heads, (cudaStream_t)stream);
+}
+
+// Reads (and clears) the hang-guard latch of every translation unit that issues tcgen05 / TMA work (csrc/tc_common.cuh).
+namespace cnb {
+int conv_tma_error_flag();        // conv_tma.cu
+int attention_tmem_error_flag();  // attention_tmem.cu
+}
+extern "C" int cnb_tc_error_flag(void) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    cnb::set_error("device error: %s", cudaGetErrorString(e));
+    return CNB_ERR_CUDA;
+  }
+  const int h = cnb::conv_tma_error_flag() | cnb::attention_tmem_error_flag();
+  if (h < 0) {
+    cnb::set_error("cudaMemcpyFromSymbol failed while reading the tcgen05 hang-guard flag");
+    return CNB_ERR_CUDA;
+  }
+  return h;
 }

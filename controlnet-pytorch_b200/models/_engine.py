@@ -45,7 +45,7 @@ def _cached(param, key, builder):
 
 
 def _tc_shape(o, i):
-    """mirror of conv2d_tc_supported (csrc/conv_tc.cu): only layers that reach the tensor core get tf32 weights."""
+    """mirror of conv2d_tma_supported (csrc/conv_tma.cu): only layers that reach the tensor core get tf32-rounded weights."""
     return i % 4 == 0 and i > 4 and o % 16 == 0      # Cin <= 4 / Cout <= 4 layers run the exact direct kernels
 
 

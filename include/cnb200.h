@@ -202,10 +202,6 @@ int cnb_nhwc_to_nchw(const void* src, int ldi, int in_coff, float* dst, int B, i
 int cnb_copy_channels(const void* src, int lds, int s_coff, void* dst, int ldd, int d_coff, long long npix,
                       int C, int elt, cnb_stream_t stream);
 
-/* Self-test of the tcgen05 GEMM pipeline on an M x N x K problem (A [M,K], W [N,K], out [M,N], all fp32 device
- * buffers); returns CNB_ERR_TIMEOUT if an mbarrier wait exceeded its guard instead of hanging. */
-int cnb_tc_gemm_selftest(const float* a, const float* w, float* out, int M, int N, int K, int mode,
-                         cnb_stream_t stream);
 /* Reads (and clears) the device-side hang-guard flag set by tcgen05 kernels; synchronises the device. */
 int cnb_tc_error_flag(void);
 
