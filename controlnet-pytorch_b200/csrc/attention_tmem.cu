@@ -183,11 +183,15 @@ __device__ __forceinline__ float chunk_max(const uint32_t* r, int vk) {
 // written against the old reference.  Warp-uniform control flow (tcgen05.ld / st are .sync.aligned).
 template <int NV>
 __device__ __forceinline__ void rescale_rows(float& m, float tm, float lazy, float c, bool first, uint32_t t_o, uint32_t t_s,
-                                             int nwritten) {
+                                             int nwritten, uint64_t* o_bar, uint32_t o_par, volatile int* abort_flag) {
   const float m_new = tm > m + lazy ? tm : m;
   const float f = ex2f((m - m_new) * c);                    // 1 for the lanes that keep their reference
   m = m_new;
   if (!first) {
+    if (o_bar != nullptr) {                                 // geometry B2: PV of the previous tile may still be in flight
+      mbar_wait_parked(o_bar, o_par, abort_flag);
+      tc_fence_after();
+    }
 #pragma unroll
     for (int cb = 0; cb < NV; cb += 16) {
       uint32_t o[16];
@@ -218,7 +222,8 @@ __device__ __forceinline__ void rescale_rows(float& m, float tm, float lazy, flo
 // `vk_tile` valid keys, whole chunks beyond them are skipped (the PV MMA skips the same 16-key blocks).
 template <int BK, int NV, int POLY, bool LAST>
 __device__ __forceinline__ void softmax_tile(float& m, bool first_tile, int vk_tile, float c, float lazy, uint32_t t_s,
-                                             uint32_t t_o) {
+                                             uint32_t t_o, uint64_t* o_bar = nullptr, uint32_t o_par = 0,
+                                             volatile int* abort_flag = nullptr) {
   constexpr int NCH = (BK + 31) / 32;
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
@@ -237,7 +242,7 @@ __device__ __forceinline__ void softmax_tile(float& m, bool first_tile, int vk_t
     if (first_tile && ch == 0) {
       m = tm;
     } else if (__any_sync(0xffffffffu, tm > m + lazy)) {
-      rescale_rows<NV>(m, tm, lazy, c, first_tile, t_o, t_s, ch);
+      rescale_rows<NV>(m, tm, lazy, c, first_tile, t_o, t_s, ch, o_bar, o_par, abort_flag);
     }
     const float mc = m * c;
     uint32_t pk[16];
