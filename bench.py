@@ -580,6 +580,30 @@ def run_b200(args):
                         "one NCCL all_gather_into_tensor of the final samples" if (world > 1 and strong) else "no collective",
                         total, "" if k_e2e == STEPS_PER_SAMPLE else "; scaled to 1000 timesteps/sample"))}
 
+    # ---- the reference TOOL's own loop on the drop-in classes (tools/sample_ddpm_controlnet.py:43-51), rank 0 -------------
+    #   per step: model(xt, t(1,), hints) + scheduler.sample_prev_timestep(xt, eps, t) with the reference's default noise
+    #   (torch.randn on the CPU generator + H2D copy, linear_noise_scheduler.py:71) - what a user gets by only swapping
+    #   the imports, without the graph-replayed sampler
+    e2e_dropin = None
+    if rank == 0 and not args.no_dropin:
+        k_d = max(5, min(args.steps, 20))
+        with torch.no_grad():
+            xt = xh.to(dev)
+            for i in reversed(range(STEPS_PER_SAMPLE - 2, STEPS_PER_SAMPLE)):          # warm
+                eps_ = model(xt, torch.as_tensor(i).unsqueeze(0).to(dev), hint)
+                xt, _ = sched.sample_prev_timestep(xt, eps_, torch.as_tensor(i).to(dev))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in reversed(range(STEPS_PER_SAMPLE - 2 - k_d, STEPS_PER_SAMPLE - 2)):
+                eps_ = model(xt, torch.as_tensor(i).unsqueeze(0).to(dev), hint)
+                xt, _ = sched.sample_prev_timestep(xt, eps_, torch.as_tensor(i).to(dev))
+            torch.cuda.synchronize()
+            dt_d = (time.perf_counter() - t0) / k_d
+        e2e_dropin = {"value": round(B / (dt_d * STEPS_PER_SAMPLE), 3), "unit": UNIT, "ms_per_step": round(dt_d * 1e3, 3),
+                      "batch": B, "timesteps_run": k_d,
+                      "note": "reference tool loop on the drop-in ControlNet + LinearNoiseScheduler of this rank's shard (eager "
+                              "launches, CPU torch.randn + H2D per step, as tools/sample_ddpm_controlnet.py:43-51), wall clock"}
+
     # ---- roofline of the dominant kernel family + CPU / stock-PyTorch baselines (rank 0) ------------------------
     roofline, fam = None, None
     cpu_baseline, tcr = None, None
@@ -623,7 +647,7 @@ def run_b200(args):
                            "sample_steps_per_sec": round(total / (ms_per_step * 1e-3), 1),
                            "model_tflops": round(total * flop_step / (ms_per_step * 1e-3) / 1e12, 2),
                            "flop_per_sample_step": flop_step},
-                "e2e": e2e, "gpu_launches": int(launches), "launches_per_step": int(launches // args.steps),
+                "e2e": e2e, "e2e_dropin": e2e_dropin, "gpu_launches": int(launches), "launches_per_step": int(launches // args.steps),
                 "roofline": roofline, "kernel_families": fam, "cpu_baseline": cpu_baseline,
                 "torch_cuda_reference": tcr, "clocks": clk.summary(w0, w1)}
         if other is not None:
@@ -652,6 +676,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the second (weak / strong) record at N > 1")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the reference-tool-loop measurement (e2e_dropin)")
     args = ap.parse_args()
     if args.mode == "tf32":
         args.mode = "f16"
