@@ -186,6 +186,10 @@ def kernel_breakdown(model, sched, x, hint, n_steps=2):
         for k_ in ("ms", "flops", "bytes"):
             f[k_] /= n_steps
         f["launches"] //= n_steps
+        for sh in f["shapes"].values():                     # per step, like the family totals they are compared with
+            for k_ in ("ms", "flops", "bytes", "scores"):
+                sh[k_] /= n_steps
+            sh["launches"] = max(1, sh["launches"] // n_steps)
     return fams, t0.elapsed_time(t1) / n_steps
 
 
