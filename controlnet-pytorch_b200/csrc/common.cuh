@@ -48,7 +48,10 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)
 // saturated value only distorts its own group (tests/test_models_gpu.py::test_f16_mode_activation_range).  Two FMNMX per
 // pair on a store-bound epilogue: below measurement noise on the step.
 __device__ __forceinline__ __half2 h2_sat(float x, float y) {
-  return __floats2half2_rn(fminf(fmaxf(x, -65504.f), 65504.f), fminf(fmaxf(y, -65504.f), 65504.f));
+  // clamp AFTER the conversion (two packed min / max instead of four scalar ones): round-to-nearest maps everything
+  // below 65520 to <= 65504 already, and what it maps to +-inf is exactly what the clamp brings back to +-65504
+  const __half2 lim = __floats2half2_rn(65504.f, 65504.f);
+  return __hmax2(__hmin2(__floats2half2_rn(x, y), lim), __hneg2(lim));
 }
 
 

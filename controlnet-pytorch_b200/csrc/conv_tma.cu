@@ -57,11 +57,13 @@ static int pick_bn(int cout) {
   return 0;
 }
 
-// widest swizzle span whose channel chunk divides Cin
+// widest swizzle span whose channel chunk divides Cin; channel counts that are whole 16-byte units but not a multiple of
+// the narrowest chunk (fp16: Cin % 16 == 8) take 32-byte chunks with a partial last one - TMA zero-fills the channels
+// past Cin, so whatever weight columns the chunk covers there multiply zeros
 static int pick_rb(int cin, int elt) {
   for (int rb = 128; rb >= 32; rb >>= 1)
     if (cin % (rb / elt) == 0) return rb;
-  return 0;
+  return (cin * elt) % 16 == 0 ? 32 : 0;
 }
 
 static int g_tma_enabled = -1;
@@ -144,10 +146,10 @@ int conv2d_tma(const cnb_conv_params* p, cudaStream_t st) {
       R = BM / Wp;
       const int tiles_y = ceil_div(p->H, R);
       const double useful = (double)p->H * p->W / ((double)tiles_y * BM);
-      const int nkb_all = 9 * (p->Cin / kc) + (p->in2 ? ceil_div(p->Cin2, kc) : 0);
+      const int nkb_all = 9 * ceil_div(p->Cin, kc) + (p->in2 ? ceil_div(p->Cin2, kc) : 0);
       const int b_res = (nkb_all * bn_h * rb + 1023) / 1024 * 1024;
       halo_stage = ((BM + 2 * Wp + 2) * rb + 1023) / 1024 * 1024;
-      const int room = SMEM_BUDGET - 1024 - 36864 - 256 - b_res;
+      const int room = SMEM_BUDGET - 1024 - 36864 - 512 - b_res;
       halo = useful >= 0.7 && room >= 3 * halo_stage && (long long)p->B * tiles_y >= 2 * g_num_sms;
     }
   }
@@ -281,13 +283,45 @@ int conv2d_tma(const cnb_conv_params* p, cudaStream_t st) {
       return CNB_ERR_CUDA;
     }
   }
+  // ---- dense fp16 output (+ fp16 residual): the epilogue stores / fetches 32-row x SLAB-column boxes by TMA (EPI 6)
+  {
+    static int epi_tma = -1;
+    if (epi_tma < 0) {
+      const char* e = getenv("CNB_CONV_EPI_TMA");
+      epi_tma = e ? atoi(e) : 1;
+    }
+    const bool dense = !halo && p->oy_mul == 1 && p->ox_mul == 1 && p->oy_add == 0 && p->ox_add == 0 &&
+                       p->OHf * p->OWf == p->OH * p->OW;
+    const bool simple = dense && p->act == 0 && !(p->temb && p->temb_per_sample);
+    const bool res_ok = !p->residual || (p->res_dtype == 1 && p->ldr % 8 == 0 && p->res_coff % 8 == 0);
+    if (epi_tma && half && simple && p->out_dtype == 1 && p->ldo % 8 == 0 && p->out_coff % 8 == 0 && res_ok) {
+      const int slab = bn % 64 == 0 ? 32 : 16;
+      const CUtensorMapSwizzle sw_o = slab == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+      const cuuint64_t dims[2] = {(cuuint64_t)p->Cout, (cuuint64_t)p->B * p->OH * p->OW};
+      const cuuint32_t box[2] = {(cuuint32_t)slab, 32u};
+      const cuuint32_t estr[2] = {1, 1};
+      const cuuint64_t so[1] = {(cuuint64_t)p->ldo * 2};
+      void* ob = reinterpret_cast<char*>(p->out) + (size_t)p->out_coff * 2;
+      CUresult r = g_encode_tiled(&a.map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ob, dims, so, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw_o, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r == CUDA_SUCCESS && p->residual) {
+        const cuuint64_t sr[1] = {(cuuint64_t)p->ldr * 2};
+        void* rb_ = const_cast<char*>(reinterpret_cast<const char*>(p->residual) + (size_t)p->res_coff * 2);
+        r = g_encode_tiled(&a.map_res, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, rb_, dims, sr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw_o, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
+      a.tma_epi = r == CUDA_SUCCESS ? 1 : 0;                 // on failure the register / shared-memory epilogue runs
+    }
+  }
   a.bias = p->bias; a.temb = p->temb; a.residual = p->residual; a.out = p->out;
   a.M = p->B * p->OH * p->OW; a.OHW = p->OH * p->OW; a.OW = p->OW;
   a.OHf = p->OHf; a.OWf = p->OWf;
   a.oy_mul = p->oy_mul; a.oy_add = p->oy_add; a.ox_mul = p->ox_mul; a.ox_add = p->ox_add;
   a.Cout = p->Cout; a.ldo = p->ldo; a.out_coff = p->out_coff; a.ldr = p->ldr; a.res_coff = p->res_coff;
   a.temb_ld = p->temb_ld; a.temb_per_sample = p->temb_per_sample; a.act = p->act; a.out_f16 = p->out_dtype == 1; a.res_f16 = p->res_dtype == 1;
-  a.Cin = p->Cin; a.ntaps = p->ntaps; a.kchunks = p->Cin / kc;
+  a.Cin = p->Cin; a.ntaps = p->ntaps; a.kchunks = ceil_div(p->Cin, kc);
   a.stride = p->stride; a.lower_w = dxmin; a.lower_h = dymin;
   a.tiles_m = halo ? p->B * a.tiles_y : ceil_div(a.M, BM); a.tiles_n = p->Cout / bn;
   return half ? conv_tma_launch_f16(rb, bn, a, g_num_sms, st) : conv_tma_launch_tf32(rb, bn, a, g_num_sms, st);

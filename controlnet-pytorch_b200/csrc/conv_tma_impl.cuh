@@ -39,6 +39,8 @@ struct alignas(64) TmaArgs {
   CUtensorMap map_a;
   CUtensorMap map_a2;   // optional second input (one (0,0) tap appended to K); used when kchunks2 > 0
   CUtensorMap map_b;
+  CUtensorMap map_out;  // EPI 6: fp16 output rows [M][Cout] (pitch ldo), box {SLAB, 32}, swizzle = row bytes
+  CUtensorMap map_res;  // EPI 6: fp16 residual rows, same box
   const float* bias;
   const float* temb;
   const void* residual;
@@ -58,6 +60,8 @@ struct alignas(64) TmaArgs {
   int s_run;        // ring depth actually used (<= Cfg::S)
   int ring_off, stage_bytes, epi_off, bar_off;
   int epi_alt;      // 1 = the two epilogue warp groups alternate TILES (short-K layers), 0 = they split a tile's columns
+  int tma_epi;      // 1 = host built map_out (/ map_res): the dense fp16 epilogue may run through TMA (EPI 6)
+  int epi_nbuf;     // EPI 6: staging buffers per epilogue warp (2 or 3)
   uint32_t tap_off[CNB_MAX_TAPS];   // offset_w | offset_h << 16
 };
 
@@ -84,6 +88,16 @@ __device__ __forceinline__ float4 ld_half4(const __half* p) {
   return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
+__device__ __forceinline__ void tma_store_2d(const void* map, uint32_t src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(x), "r"(y)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 constexpr int pow2_at_least(int v, int p = 32) { return p >= v ? p : pow2_at_least(v, p * 2); }
 
 // RB = bytes of K per smem row = the swizzle span: 128 (SWIZZLE_128B), 64 (SWIZZLE_64B) or 32 (SWIZZLE_32B); a stage holds
@@ -96,7 +110,12 @@ struct Cfg {
   static constexpr int EPI_BYTES = EPI_WARPS * 32 * SLAB_STRIDE * 4;
   static constexpr int B_STAGE_BYTES = BN * RB;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 512;                   // ring / accumulator barriers + 3 per epilogue warp (EPI 6)
+  // EPI 6 (dense fp16 out through TMA): per epilogue warp NB staging buffers of 32 rows x SLAB fp16 (swizzled rows of
+  // SLAB * 2 bytes) + the bias (+ time-embedding row) of the slabs the warp owns; NB = 2 fits EPI_BYTES for every BN
+  static constexpr int E6_BUF = 32 * SLAB * 2;
+  static constexpr int E6_BIAS = (((BN / SLAB + 1) / 2) * SLAB * 4 + 511) / 512 * 512;
+  __host__ __device__ static constexpr int e6_warp_bytes(int nb) { return nb * E6_BUF + E6_BIAS; }
   static constexpr int S_RAW = (SMEM_BUDGET - 1024 - EPI_BYTES - BAR_BYTES) / STAGE_BYTES;
   static constexpr int S = S_RAW > 8 ? 8 : S_RAW;
   static constexpr int EPI_OFFSET = S * STAGE_BYTES;
@@ -105,6 +124,7 @@ struct Cfg {
   static constexpr int ACC_STRIDE = pow2_at_least(BN);
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static_assert(S >= 2, "pipeline needs at least two stages");
+  static_assert(EPI_WARPS * (2 * E6_BUF + E6_BIAS) <= EPI_BYTES, "EPI 6 staging (two buffers) must fit the epilogue area");
   static_assert(TMEM_COLS <= 512, "accumulators exceed TMEM");
   static_assert(A_STAGE_BYTES % (8 * RB) == 0 && B_STAGE_BYTES % (8 * RB) == 0,
                 "operand tiles must keep swizzle-atom alignment (8 rows x RB bytes)");
@@ -112,7 +132,7 @@ struct Cfg {
 
 // EPI selects the epilogue: 0 = dense fp32 out, 1 = dense fp32 out + fp32 residual, 2 = dense fp16 out,
 // 4 = dense fp16 out + fp16 residual (the fp16 activation stream), 5 = halo tiles with fp16 out (+ fp16 residual),
-// 3 = generic.
+// 6 = dense fp16 out (+ fp16 residual) staged per warp and moved by TMA (the default for the fp16 stream), 3 = generic.
 template <int BN, bool HALF, int EPI, int RB>
 __global__ void __launch_bounds__(NUM_THREADS, (BN <= 128 && EPI != 3) ? 2 : 1)   // two CTAs per SM: <= 102 registers
 conv_tma_kernel(const __grid_constant__ TmaArgs a) {
@@ -142,6 +162,7 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
   const uint32_t stage_bytes = (uint32_t)a.stage_bytes;
   const bool bres = a.bres != 0;
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  uint64_t* e6_bar = reinterpret_cast<uint64_t*>(smem + a.bar_off + 192);   // [EPI_WARPS][3] residual landed (EPI 6)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -159,6 +180,8 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
       mbar_init(&tempty_bar[i], a.epi_alt ? EPI_WARPS / 2 : EPI_WARPS);
     }
     mbar_init(bres_bar, 1);
+    if (EPI == 6)
+      for (int i = 0; i < EPI_WARPS * 3; ++i) mbar_init(&e6_bar[i], 1);
     *abort_flag = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -324,6 +347,149 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
     const int ew = warp - 2;
     const int q = warp & 3;
     const int par = ew >> 2;
+    if constexpr (EPI == 6) {
+      // ---- dense fp16 output (+ fp16 residual) through TMA.  A lane owns one accumulator row (tcgen05.ld 32x32b), so a
+      // slab of SLAB columns is SLAB * 2 contiguous bytes per lane: it goes bias-added and packed into a per-warp staging
+      // buffer (rows swizzled like the tensor map: 16-byte stores of eight lanes hit eight different bank groups) and
+      // leaves as ONE cp.async.bulk.tensor store of the 32 x SLAB box; the residual box arrives the same way, one slab
+      // ahead, into the buffer it is then added to in place.  No transposing round trip through shared memory, no
+      // per-row address arithmetic, no global-load latency inside the per-slab chain; the M tail is the tensor map's.
+      constexpr int NSLAB = BN / SLAB;
+      constexpr int ROWB = SLAB * 2;
+      constexpr int BUF = C::E6_BUF;
+      constexpr int CH = ROWB / 16;                            // 16-byte chunks per staged row
+      const int nb = a.epi_nbuf;
+      const uint32_t wb_off = (uint32_t)a.epi_off + (uint32_t)ew * (uint32_t)C::e6_warp_bytes(nb);
+      uint8_t* wbase = smem + wb_off;
+      const uint32_t wbase_u = smem_base + wb_off;
+      float* bias_s = reinterpret_cast<float*>(wbase + nb * BUF);
+      uint64_t* rbar = e6_bar + ew * 3;
+      const bool has_res = a.residual != nullptr;
+      const float* bias = a.bias;
+      const float* temb_row = (a.temb && !a.temb_per_sample) ? a.temb : nullptr;
+      const bool has_bias = bias != nullptr || temb_row != nullptr;
+      const int M = a.M, tiles_n = a.tiles_n;
+      const int si0 = par, sstep = 2;                          // the two warps of a lane quarter split the slabs by parity
+      const bool has_items = si0 < NSLAB;
+      const int sw = SLAB == 32 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);   // SWIZZLE_64B / _32B pattern of this lane's row
+      auto issue_res = [&](int tile_, int si_, int buf_) {     // lane 0: residual box of one (tile, slab) -> buffer buf_
+        const int mt_ = tile_ / tiles_n, nt_ = tile_ - mt_ * tiles_n;
+        const int m_ = mt_ * BM + q * 32;
+        if (m_ < M) {
+          mbar_expect_tx(&rbar[buf_], (uint32_t)BUF);
+          tma_load_2d(wbase_u + (uint32_t)(buf_ * BUF), &a.map_res, &rbar[buf_], nt_ * BN + si_ * SLAB, m_);
+        }
+      };
+      int cb = 0;                                              // staging buffer of the current slab
+      uint32_t rphase = 0;                                     // bit b: parity of the next completion of rbar[b]
+      int last_nt = -1, tcount = 0;
+      int tile = blockIdx.x;
+      if (has_res && has_items && tile < ntiles && lane == 0) issue_res(tile, si0, 0);
+      bool ok = true;
+      for (; tile < ntiles && ok; tile += gridDim.x, ++tcount) {
+        const int mt = tile / tiles_n, nt = tile - mt * tiles_n;
+        const int m_w = mt * BM + q * 32;
+        const int n0 = nt * BN;
+        if (has_items && has_bias && nt != last_nt) {          // bias (+ time-embedding row) of this warp's slabs
+          __syncwarp();
+          int k = 0;
+          for (int si = si0; si < NSLAB; si += sstep, ++k) {
+            if (lane < SLAB) {
+              const int n = n0 + si * SLAB + lane;
+              float v = bias ? __ldg(bias + n) : 0.f;
+              if (temb_row) v += __ldg(temb_row + n);
+              bias_s[k * SLAB + lane] = v;
+            }
+          }
+          last_nt = nt;
+          __syncwarp();
+        }
+        const int acc = tcount & 1;
+        if (!mbar_wait(&tfull_bar[acc], (uint32_t)((tcount >> 1) & 1), abort_flag)) break;
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (uint32_t)(acc * C::ACC_STRIDE) + ((uint32_t)(q * 32) << 16);
+        if (!has_items) {                                      // single-slab tiles: the odd warps have nothing to read
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          continue;
+        }
+        const bool rows_valid = m_w < M;                       // warp-uniform: the whole 32-row box is past the M tail
+        int k = 0;
+#pragma unroll 1
+        for (int si = si0; si < NSLAB; si += sstep, ++k) {
+          uint32_t r[SLAB];
+#pragma unroll
+          for (int j = 0; j < SLAB / 16; ++j) tmem_ld16_nowait(t_addr + (uint32_t)(si * SLAB + 16 * j), r + 16 * j);
+          if (lane == 0) {
+            if (has_res) {
+              // the slab after this one (possibly of the next tile): its buffer was last read by the store nb slabs back
+              int ntile = tile, nsi = si + sstep;
+              if (nsi >= NSLAB) { ntile = tile + gridDim.x; nsi = si0; }
+              if (ntile < ntiles) {
+                if (nb == 2) bulk_wait_read<0>(); else bulk_wait_read<1>();
+                issue_res(ntile, nsi, cb + 1 == nb ? 0 : cb + 1);
+              }
+            } else {
+              if (nb == 2) bulk_wait_read<1>(); else bulk_wait_read<2>();   // the store that last read buffer cb
+            }
+          }
+          tmem_ld_wait();
+          if (si + sstep >= NSLAB) {                           // this warp's last slab: hand its share of the accumulator back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          if (rows_valid) {
+            if (has_res) {
+              ok = mbar_wait(&rbar[cb], (rphase >> cb) & 1u, abort_flag);
+              rphase ^= 1u << cb;
+              if (!ok) break;
+            } else {
+              __syncwarp();                                    // lane 0 has seen buffer cb released
+            }
+            uint8_t* row = wbase + cb * BUF + lane * ROWB;
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + k * SLAB);
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+              uint4* cell = reinterpret_cast<uint4*>(row + ((j ^ sw) << 4));
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * j + e]);
+              if (has_bias) {
+                const float4 b0 = b4[2 * j], b1 = b4[2 * j + 1];
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              if (has_res) {
+                const uint4 rr = *cell;
+                const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rw[e]));
+                  v[2 * e] += f.x; v[2 * e + 1] += f.y;
+                }
+              }
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __half2 h = h2_sat(v[2 * e], v[2 * e + 1]);
+                o[e] = *reinterpret_cast<const uint32_t*>(&h);
+              }
+              *cell = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            fence_proxy_async();
+          }
+          __syncwarp();
+          if (lane == 0) {
+            if (rows_valid) tma_store_2d(&a.map_out, wbase_u + (uint32_t)(cb * BUF), n0 + si * SLAB, m_w);
+            bulk_commit();                                     // an empty group for skipped boxes keeps the group count in step
+          }
+          cb = cb + 1 == nb ? 0 : cb + 1;
+        }
+      }
+      if (lane == 0) bulk_wait_all();                          // the staging buffers must outlive the stores' reads
+      tc_fence_before();
+    } else {
     float* slab = reinterpret_cast<float*>(smem + a.epi_off) + (size_t)ew * 32 * SSTR;
     constexpr int NSLAB = BN / SLAB;
     constexpr int LPR = SLAB / 4;                             // lanes per row in the coalesced pass
@@ -504,6 +670,7 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
       }
     }
     tc_fence_before();
+    }
   }
   __syncthreads();
   if (warp == 1) {
@@ -594,6 +761,20 @@ static int launch_epi(const TmaArgs& a_in, int num_sms, cudaStream_t st) {
   }
   size_t smem_bytes;
   a.bar_off = a.epi_off + C::EPI_BYTES;
+  if (EPI == 6) {
+    // a third staging buffer per epilogue warp where shared memory is left over: the residual box of slab i+1 can then
+    // be requested while the store of slab i-1 is still reading its buffer
+    static int nbuf_env = -1;
+    if (nbuf_env < 0) {
+      const char* e = getenv("CNB_CONV_EPI_NBUF");
+      nbuf_env = e ? atoi(e) : 0;
+    }
+    const int budget = two ? 112 * 1024 : SMEM_BUDGET;
+    const int e6_3 = EPI_WARPS * C::e6_warp_bytes(3);
+    const bool fits3 = a.epi_off + e6_3 + C::BAR_BYTES + 1024 <= budget;
+    a.epi_nbuf = (nbuf_env == 2 || !fits3) ? 2 : 3;
+    if (a.epi_nbuf == 3 && e6_3 > C::EPI_BYTES) a.bar_off = a.epi_off + e6_3;
+  }
   {
     // alternate-tile epilogue when a tile's tensor work (~BN * K / 32 cycles) is shorter than its epilogue
     static int alt_env = -2;
@@ -605,6 +786,7 @@ static int launch_epi(const TmaArgs& a_in, int num_sms, cudaStream_t st) {
     // measured (B = 1024): halo 3x3 16->16 @28 54 -> 44 us, 64->64 @28 97 -> 91, 32->64 @28 89 -> 83; dense 1x1 layers
     // with several column slabs lose (256->768 @7 40 -> 44 us), so only the halo layers switch
     a.epi_alt = alt_env >= 0 ? alt_env : ((a.halo && (long long)BN * ktot < 131072) ? 1 : 0);
+    if (EPI == 6) a.epi_alt = 0;
   }
   smem_bytes = (size_t)a.bar_off + C::BAR_BYTES + 1024;
   CNB_CUDA(launch_pdl((long long)ntiles * 128 * BN, conv_tma_kernel<BN, HALF, EPI, RB>, dim3(grid), dim3(NUM_THREADS), smem_bytes, st, a));
@@ -621,6 +803,9 @@ static int launch(const TmaArgs& a, int num_sms, cudaStream_t st) {
     return launch_epi<BN, HALF, 5, RB>(a, num_sms, st);
   if (simple && !a.out_f16 && !a.residual) return launch_epi<BN, HALF, 0, RB>(a, num_sms, st);
   if (simple && !a.out_f16 && a.residual && !a.res_f16) return launch_epi<BN, HALF, 1, RB>(a, num_sms, st);
+  if constexpr (HALF) {
+    if (simple && a.out_f16 && a.tma_epi && (!a.residual || a.res_f16)) return launch_epi<BN, HALF, 6, RB>(a, num_sms, st);
+  }
   if (simple && a.out_f16 && !a.residual) return launch_epi<BN, HALF, 2, RB>(a, num_sms, st);
   if (simple && a.out_f16 && a.residual && a.res_f16) return launch_epi<BN, HALF, 4, RB>(a, num_sms, st);
   return launch_epi<BN, HALF, 3, RB>(a, num_sms, st);

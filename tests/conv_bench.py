@@ -76,8 +76,8 @@ if what in ("attn", "all"):
                    (1024, 384, 16), (1024, 128, 16), (256, 512, 16), (64, 768, 16)]   # last four: CelebHQ LDM levels
         if os.environ.get("CB_SHAPES"):                        # "L,E,heads[,batch];..." (batch defaults to CB_BATCH)
             ashapes = [tuple(int(v) for v in t.split(",")) for t in os.environ["CB_SHAPES"].split(";")]
-        if os.environ.get("CB_ONLY"):
-            ashapes = [ashapes[int(i)] for i in os.environ["CB_ONLY"].split(",")]
+        if os.environ.get("CB_ONLY_ATTN", os.environ.get("CB_ONLY")):
+            ashapes = [ashapes[int(i)] for i in os.environ.get("CB_ONLY_ATTN", os.environ.get("CB_ONLY")).split(",")]
         for shp in ashapes:
             L, E, heads = shp[:3]
             side = int(math.isqrt(L))
