@@ -108,6 +108,9 @@ def k_heads(a, k):
     return a[1] if len(a) > 1 else k.get("heads", 1)
 
 
+LAST_ORDINALS = []      # (process-wide launch ordinal, family, shape) of the launches kernel_breakdown timed last
+
+
 def kernel_breakdown(model, sched, x, hint, n_steps=2):
     import torch
     ops = importlib.import_module("controlnet-pytorch_b200.ops")
@@ -115,13 +118,19 @@ def kernel_breakdown(model, sched, x, hint, n_steps=2):
     rec = []
     orig = {k: getattr(ops, k) for k in ("conv", "groupnorm", "attention", "sched_step")}
 
+    rtm = importlib.import_module("controlnet-pytorch_b200.runtime")
+    count = rtm.lib().cnb_launch_count
+
     def timed(name, meta_fn, fn):
         def w(*a, **k):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            first = int(count())                    # ordinal of this call's first libcnb200 launch in the process
             e0.record()
             out = fn(*a, **k)
             e1.record()
-            rec.append((name, meta_fn(out, a, k), e0, e1))
+            meta = meta_fn(out, a, k)
+            meta["ordinal"] = first
+            rec.append((name, meta, e0, e1))
             return out
         return w
 
@@ -169,7 +178,9 @@ def kernel_breakdown(model, sched, x, hint, n_steps=2):
         for k_, v in orig.items():
             setattr(ops, k_, v)
     fams = {}
+    LAST_ORDINALS.clear()
     for name, meta, e0, e1 in rec:
+        LAST_ORDINALS.append((meta["ordinal"], meta["fam"], meta.get("shape", "?")))
         ms = e0.elapsed_time(e1)
         f = fams.setdefault(meta["fam"], dict(ms=0.0, flops=0.0, bytes=0.0, launches=0, shapes={}))
         f["ms"] += ms

@@ -47,6 +47,29 @@ __device__ __forceinline__ void cp_async(uint32_t dst, const void* src, uint32_t
   else
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// mbarrier helpers of the warp-decoupled pipeline (MB): a hung pipeline traps instead of hanging the GPU
+__device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mb_arrive_cp_async(uint64_t* bar) {     // arrives when this thread's prior cp.asyncs landed
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+  for (int spin = 0; spin < (1 << 20); ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(addr), "r"(parity), "r"(4000u) : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -79,11 +102,11 @@ __host__ __device__ constexpr int attn_sub(int D, int BK, int NW) { return (ATTN
 #ifndef ATTN_MIN_BLOCKS
 #define ATTN_MIN_BLOCKS 7
 #endif
-template <int D, int BK, int NW, bool H2>
+template <int D, int BK, int NW, bool H2, int HALVES, bool MB>
 #ifndef ATTN_MIN_BLOCKS8
 #define ATTN_MIN_BLOCKS8 3   // 8-warp kernels: <= 85 registers (d = 24: 122 -> 80, L = 1024 launch 2.15 -> 1.97 ms)
 #endif
-__global__ void __launch_bounds__(NW * 32, (NW == 4 && D <= 16) ? ATTN_MIN_BLOCKS : (NW == 8 ? ATTN_MIN_BLOCKS8 : 0))
+__global__ void __launch_bounds__(NW * 32, (NW == 4 && D <= 16) ? (HALVES == 2 ? 8 : ATTN_MIN_BLOCKS) : (NW == 8 ? (HALVES == 2 ? 4 : ATTN_MIN_BLOCKS8) : 0))
 attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int L, int E, float scale_log2) {
   constexpr int d = D;
   constexpr int DP = (D + 15) / 16 * 16;         // K extent of Q K^T
@@ -110,11 +133,22 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
   const __half* base = qkv + (size_t)b * L * row3 + (size_t)h * d;
   const uint32_t smem_u = (uint32_t)__cvta_generic_to_shared(smem);
 
+  // MB: warp-decoupled ring.  full[s] completes when every thread's cp.asyncs of the tile in slot s have landed, empty[s]
+  // when every warp has finished reading it - no block barrier in the tile loop, a warp only ever waits for data, or
+  // for a warp that is more than a tile behind (ncu: 15 % of the stall samples of the barrier version sat at BAR.SYNC)
+  __shared__ uint64_t mb_full[3], mb_empty[3];
+  if (MB) {
+    if (tid == 0) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { mb_init(&mb_full[i], THREADS); mb_init(&mb_empty[i], NW); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
   // zero the pad columns once (cp.async only ever writes the d real columns)
   if (d < DP) {
     for (int i = tid; i < NSLOT * 2 * TILE / 2; i += THREADS) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
-    __syncthreads();
   }
+  if (MB || d < DP) __syncthreads();
 
   // ---- Q fragments, kept in registers for the whole kernel
   uint32_t qf[KS][4];
@@ -216,11 +250,12 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
   // one key tile; MASK = the (only) tile that may contain keys >= L; NG = 16-key groups of the tile that hold any
   // valid key (the ragged last tile skips its fully padded groups: 784 = 12 x 64 + 16 keys costs 12.25 tiles, not 13)
   int cur_slot = 0;                              // ring slot of the tile being consumed (advanced by the main loop)
-  auto tile_body = [&](int t, auto mask_tag, auto ng_tag) {
+  auto tile_body = [&](int t, auto mask_tag, auto ng_tag, auto g0_tag) {
     constexpr bool MASK = decltype(mask_tag)::value;
     constexpr int NG = decltype(ng_tag)::value;
+    constexpr int G0 = decltype(g0_tag)::value;    // first 16-key group of the tile this call covers
     constexpr int NTA = NG * 2;                    // active S column tiles
-    const uint32_t sK = smem_u + (uint32_t)(cur_slot * 2 * TILE) * 2u;
+    const uint32_t sK = smem_u + (uint32_t)(cur_slot * 2 * TILE) * 2u + (uint32_t)(G0 * 16 * STRIDE) * 2u;
     const uint32_t sV = sK + (uint32_t)TILE * 2u;
 
     // ---- S = Q K^T  (16 x BK per warp)
@@ -238,7 +273,7 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
       }
     }
     if (MASK) {
-      const int kbase = t * BK;
+      const int kbase = t * BK + G0 * 16;
 #pragma unroll
       for (int nt = 0; nt < NTA; ++nt) {
         const int key = kbase + nt * 8 + 2 * q4;
@@ -309,30 +344,78 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
   // warp has finished group g-1, whose slots are exactly the ones group g+2 is loaded into right after it.
   const bool active = q0 < L;
   const int ngroups = (ntiles + SUB - 1) / SUB;
-  load_group(0);
-  if (ngroups > 1) load_group(1);
+  static_assert(!MB || SUB == 1, "the mbarrier ring carries one tile per slot");
+  uint32_t ld_par = 0, cur_par = 0;              // MB: phase parities of the slot being loaded / consumed
+  auto load_tile_mb = [&]() {                    // MB: tile ld_t into slot ld_slot once every warp has released it
+    const int slot = ld_slot;
+    if (ld_t >= 3) mb_wait(&mb_empty[slot], ld_par ^ 1u);
+    load_tile();                                 // advances ld_t / ld_slot
+    mb_arrive_cp_async(&mb_full[slot]);
+    if (ld_slot == 0) ld_par ^= 1u;
+  };
+  if (MB) {
+    load_tile_mb();
+    if (ntiles > 1) load_tile_mb();
+  } else {
+    load_group(0);
+    if (ngroups > 1) load_group(1);
+  }
   const bool ragged = (L % BK) != 0;
   for (int grp = 0; grp < ngroups; ++grp) {
-    if (grp + 1 < ngroups) asm volatile("cp.async.wait_group 1;" ::: "memory");
-    else asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    if (grp + 2 < ngroups) load_group(grp + 2);
+    if (MB) {
+      mb_wait(&mb_full[cur_slot], cur_par);
+    } else {
+      if (grp + 1 < ngroups) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      if (grp + 2 < ngroups) load_group(grp + 2);
+    }
+    const int mb_slot = cur_slot;
     if (active) {                                  // warps whose 16 query rows are all padding only help with the loads
 #pragma unroll
       for (int hh = 0; hh < SUB; ++hh) {
         const int t = grp * SUB + hh;
         if (t >= ntiles) break;
+        using G0_ = std::integral_constant<int, 0>;
+        if constexpr (HALVES != 0 && BK == 64) {
+          // the tile in two 32-key halves (S of a half = 16 registers instead of 32): at 7 CTAs per SM (72 registers) the
+          // compiler otherwise re-derives every lane-dependent address from %tid inside the tile loop - ~40 % of the
+          // instructions of a tile were that bookkeeping (ncu: 7.4 issued instructions per exponential)
+          using G2_ = std::integral_constant<int, 2>;
+          using N1_ = std::integral_constant<int, 1>;
+          using N2_ = std::integral_constant<int, 2>;
+          if (ragged && t == ntiles - 1) {
+            const int groups = (L - t * BK + 15) / 16;
+            if (groups == 1) tile_body(t, std::true_type{}, N1_{}, G0_{});
+            else if (groups == 2) tile_body(t, std::true_type{}, N2_{}, G0_{});
+            else {
+              tile_body(t, std::false_type{}, N2_{}, G0_{});
+              if (groups == 3) tile_body(t, std::true_type{}, N1_{}, G2_{});
+              else tile_body(t, std::true_type{}, N2_{}, G2_{});
+            }
+          } else {
+            tile_body(t, std::false_type{}, N2_{}, G0_{});
+            tile_body(t, std::false_type{}, N2_{}, G2_{});
+          }
+        } else
         if (ragged && t == ntiles - 1) {
           const int groups = (L - t * BK + 15) / 16;
-          if (groups == 1) tile_body(t, std::true_type{}, std::integral_constant<int, 1>{});
-          if constexpr (BK >= 32) { if (groups == 2) tile_body(t, std::true_type{}, std::integral_constant<int, 2>{}); }
-          if constexpr (BK >= 48) { if (groups == 3) tile_body(t, std::true_type{}, std::integral_constant<int, 3>{}); }
-          if constexpr (BK >= 64) { if (groups == 4) tile_body(t, std::true_type{}, std::integral_constant<int, 4>{}); }
+          if (groups == 1) tile_body(t, std::true_type{}, std::integral_constant<int, 1>{}, G0_{});
+          if constexpr (BK >= 32) { if (groups == 2) tile_body(t, std::true_type{}, std::integral_constant<int, 2>{}, G0_{}); }
+          if constexpr (BK >= 48) { if (groups == 3) tile_body(t, std::true_type{}, std::integral_constant<int, 3>{}, G0_{}); }
+          if constexpr (BK >= 64) { if (groups == 4) tile_body(t, std::true_type{}, std::integral_constant<int, 4>{}, G0_{}); }
         } else {
-          tile_body(t, std::false_type{}, std::integral_constant<int, BK / 16>{});
+          tile_body(t, std::false_type{}, std::integral_constant<int, BK / 16>{}, G0_{});
         }
         if (++cur_slot == NSLOT) cur_slot = 0;
       }
+    }
+    if (MB) {
+      if (!active) { if (++cur_slot == NSLOT) cur_slot = 0; }
+      if (cur_slot == 0) cur_par ^= 1u;
+      __syncwarp();
+      if (lane == 0) mb_arrive(&mb_empty[mb_slot]);  // this warp is done with the slot
+      if (grp + 2 < ntiles) load_tile_mb();          // two tiles ahead, into the slot of the tile before this one
     }
   }
 
@@ -352,18 +435,18 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
 
 static int g_h2 = -1;   // CNB_ATTN_EXP2H=1: ex2.approx.f16x2 exponentials (no faster on sm_100a: two MUFU ops per pair)
 
-template <int D, int BK, int NW, bool H2>
+template <int D, int BK, int NW, bool H2, int HALVES, bool MB>
 static int launch2(const void* qkv, void* out, int B, int L, int E, int heads, cudaStream_t st) {
   constexpr int DP = (D + 15) / 16 * 16;
   constexpr size_t SMEM = (size_t)3 * attn_sub(D, BK, NW) * 2 * BK * (DP + 8) * sizeof(__half);
   static DeviceOnce attr_once;
   if (attr_once.first()) {
-    CNB_CUDA(cudaFuncSetAttribute(attention_f16_kernel<D, BK, NW, H2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CNB_CUDA(cudaFuncSetAttribute(attention_f16_kernel<D, BK, NW, H2, HALVES, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)SMEM));
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)D);
   dim3 grid(ceil_div(L, 16 * NW), heads, B);
-  CNB_CUDA(launch_pdl((long long)B * L * E, attention_f16_kernel<D, BK, NW, H2>, grid, dim3(NW * 32), SMEM, st,
+  CNB_CUDA(launch_pdl((long long)B * L * E, attention_f16_kernel<D, BK, NW, H2, HALVES, MB>, grid, dim3(NW * 32), SMEM, st,
                       reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(out), L, E, scale_log2));
   CNB_LAUNCH_CHECK();
   return CNB_OK;
@@ -375,8 +458,25 @@ static int launch(const void* qkv, void* out, int B, int L, int E, int heads, cu
     const char* e = getenv("CNB_ATTN_EXP2H");
     g_h2 = e ? atoi(e) : 0;
   }
-  if (D <= 32 && g_h2) return launch2<D, BK, NW, (D <= 32)>(qkv, out, B, L, E, heads, st);
-  return launch2<D, BK, NW, false>(qkv, out, B, L, E, heads, st);
+  static int halves = -1;                  // CNB_ATTN_HALVES=0: whole 64-key tiles (the round-1 kernel)
+  if (halves < 0) {
+    const char* e = getenv("CNB_ATTN_HALVES");
+    halves = e ? atoi(e) : 1;
+  }
+  if (D <= 32 && g_h2) return launch2<D, BK, NW, (D <= 32), 0, false>(qkv, out, B, L, E, heads, st);
+  // measured (profiles/r02_attention_table.md): halves pay everywhere at head dims <= 16; with them the kernel also fits
+  // 64 registers = 8 CTAs (4 warps) / 4 CTAs (8 warps) per SM, which wins or ties except at d = 16 with 4 warps (spills)
+  constexpr int HV = (BK == 64 && D <= 16) ? ((D == 16 && NW == 4) ? 1 : 2) : 0;
+  static int mbar = -1;                    // CNB_ATTN_MBAR=0: block barrier per tile instead of the mbarrier ring
+  if (mbar < 0) {
+    const char* e = getenv("CNB_ATTN_MBAR");
+    mbar = e ? atoi(e) : 1;
+  }
+  if (HV != 0 && halves == 1 && mbar) return launch2<D, BK, NW, false, HV, (HV != 0)>(qkv, out, B, L, E, heads, st);
+  if (HV != 0 && halves == 1) return launch2<D, BK, NW, false, HV, false>(qkv, out, B, L, E, heads, st);
+  if (HV != 0 && halves == 2) return launch2<D, BK, NW, false, (HV != 0 ? 2 : 0), false>(qkv, out, B, L, E, heads, st);
+  if (HV != 0 && halves == 3) return launch2<D, BK, NW, false, (HV != 0 ? 1 : 0), false>(qkv, out, B, L, E, heads, st);
+  return launch2<D, BK, NW, false, 0, false>(qkv, out, B, L, E, heads, st);
 }
 
 static inline long long padded(int L, int bq, int bk) {
