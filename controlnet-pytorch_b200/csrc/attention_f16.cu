@@ -47,29 +47,6 @@ __device__ __forceinline__ void cp_async(uint32_t dst, const void* src, uint32_t
   else
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-// mbarrier helpers of the warp-decoupled pipeline (MB): a hung pipeline traps instead of hanging the GPU
-__device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mb_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void mb_arrive_cp_async(uint64_t* bar) {     // arrives when this thread's prior cp.asyncs landed
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
-  for (int spin = 0; spin < (1 << 20); ++spin) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(addr), "r"(parity), "r"(4000u) : "memory");
-    if (ok) return;
-  }
-  __trap();
-}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -102,7 +79,7 @@ __host__ __device__ constexpr int attn_sub(int D, int BK, int NW) { return (ATTN
 #ifndef ATTN_MIN_BLOCKS
 #define ATTN_MIN_BLOCKS 7
 #endif
-template <int D, int BK, int NW, bool H2, int HALVES, bool MB>
+template <int D, int BK, int NW, bool H2, int HALVES>
 #ifndef ATTN_MIN_BLOCKS8
 #define ATTN_MIN_BLOCKS8 3   // 8-warp kernels: <= 85 registers (d = 24: 122 -> 80, L = 1024 launch 2.15 -> 1.97 ms)
 #endif
@@ -133,22 +110,11 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
   const __half* base = qkv + (size_t)b * L * row3 + (size_t)h * d;
   const uint32_t smem_u = (uint32_t)__cvta_generic_to_shared(smem);
 
-  // MB: warp-decoupled ring.  full[s] completes when every thread's cp.asyncs of the tile in slot s have landed, empty[s]
-  // when every warp has finished reading it - no block barrier in the tile loop, a warp only ever waits for data, or
-  // for a warp that is more than a tile behind (ncu: 15 % of the stall samples of the barrier version sat at BAR.SYNC)
-  __shared__ uint64_t mb_full[3], mb_empty[3];
-  if (MB) {
-    if (tid == 0) {
-#pragma unroll
-      for (int i = 0; i < 3; ++i) { mb_init(&mb_full[i], THREADS); mb_init(&mb_empty[i], NW); }
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-  }
   // zero the pad columns once (cp.async only ever writes the d real columns)
   if (d < DP) {
     for (int i = tid; i < NSLOT * 2 * TILE / 2; i += THREADS) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+    __syncthreads();
   }
-  if (MB || d < DP) __syncthreads();
 
   // ---- Q fragments, kept in registers for the whole kernel
   uint32_t qf[KS][4];
@@ -344,33 +310,14 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
   // warp has finished group g-1, whose slots are exactly the ones group g+2 is loaded into right after it.
   const bool active = q0 < L;
   const int ngroups = (ntiles + SUB - 1) / SUB;
-  static_assert(!MB || SUB == 1, "the mbarrier ring carries one tile per slot");
-  uint32_t ld_par = 0, cur_par = 0;              // MB: phase parities of the slot being loaded / consumed
-  auto load_tile_mb = [&]() {                    // MB: tile ld_t into slot ld_slot once every warp has released it
-    const int slot = ld_slot;
-    if (ld_t >= 3) mb_wait(&mb_empty[slot], ld_par ^ 1u);
-    load_tile();                                 // advances ld_t / ld_slot
-    mb_arrive_cp_async(&mb_full[slot]);
-    if (ld_slot == 0) ld_par ^= 1u;
-  };
-  if (MB) {
-    load_tile_mb();
-    if (ntiles > 1) load_tile_mb();
-  } else {
-    load_group(0);
-    if (ngroups > 1) load_group(1);
-  }
+  load_group(0);
+  if (ngroups > 1) load_group(1);
   const bool ragged = (L % BK) != 0;
   for (int grp = 0; grp < ngroups; ++grp) {
-    if (MB) {
-      mb_wait(&mb_full[cur_slot], cur_par);
-    } else {
-      if (grp + 1 < ngroups) asm volatile("cp.async.wait_group 1;" ::: "memory");
-      else asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncthreads();
-      if (grp + 2 < ngroups) load_group(grp + 2);
-    }
-    const int mb_slot = cur_slot;
+    if (grp + 1 < ngroups) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (grp + 2 < ngroups) load_group(grp + 2);
     if (active) {                                  // warps whose 16 query rows are all padding only help with the loads
 #pragma unroll
       for (int hh = 0; hh < SUB; ++hh) {
@@ -410,13 +357,6 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
         if (++cur_slot == NSLOT) cur_slot = 0;
       }
     }
-    if (MB) {
-      if (!active) { if (++cur_slot == NSLOT) cur_slot = 0; }
-      if (cur_slot == 0) cur_par ^= 1u;
-      __syncwarp();
-      if (lane == 0) mb_arrive(&mb_empty[mb_slot]);  // this warp is done with the slot
-      if (grp + 2 < ntiles) load_tile_mb();          // two tiles ahead, into the slot of the tile before this one
-    }
   }
 
   // ---- normalise and store
@@ -435,18 +375,18 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
 
 static int g_h2 = -1;   // CNB_ATTN_EXP2H=1: ex2.approx.f16x2 exponentials (no faster on sm_100a: two MUFU ops per pair)
 
-template <int D, int BK, int NW, bool H2, int HALVES, bool MB>
+template <int D, int BK, int NW, bool H2, int HALVES>
 static int launch2(const void* qkv, void* out, int B, int L, int E, int heads, cudaStream_t st) {
   constexpr int DP = (D + 15) / 16 * 16;
   constexpr size_t SMEM = (size_t)3 * attn_sub(D, BK, NW) * 2 * BK * (DP + 8) * sizeof(__half);
   static DeviceOnce attr_once;
   if (attr_once.first()) {
-    CNB_CUDA(cudaFuncSetAttribute(attention_f16_kernel<D, BK, NW, H2, HALVES, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CNB_CUDA(cudaFuncSetAttribute(attention_f16_kernel<D, BK, NW, H2, HALVES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)SMEM));
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)D);
   dim3 grid(ceil_div(L, 16 * NW), heads, B);
-  CNB_CUDA(launch_pdl((long long)B * L * E, attention_f16_kernel<D, BK, NW, H2, HALVES, MB>, grid, dim3(NW * 32), SMEM, st,
+  CNB_CUDA(launch_pdl((long long)B * L * E, attention_f16_kernel<D, BK, NW, H2, HALVES>, grid, dim3(NW * 32), SMEM, st,
                       reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(out), L, E, scale_log2));
   CNB_LAUNCH_CHECK();
   return CNB_OK;
@@ -463,20 +403,14 @@ static int launch(const void* qkv, void* out, int B, int L, int E, int heads, cu
     const char* e = getenv("CNB_ATTN_HALVES");
     halves = e ? atoi(e) : 1;
   }
-  if (D <= 32 && g_h2) return launch2<D, BK, NW, (D <= 32), 0, false>(qkv, out, B, L, E, heads, st);
+  if (D <= 32 && g_h2) return launch2<D, BK, NW, (D <= 32), 0>(qkv, out, B, L, E, heads, st);
   // measured (profiles/r02_attention_table.md): halves pay everywhere at head dims <= 16; with them the kernel also fits
   // 64 registers = 8 CTAs (4 warps) / 4 CTAs (8 warps) per SM, which wins or ties except at d = 16 with 4 warps (spills)
   constexpr int HV = (BK == 64 && D <= 16) ? ((D == 16 && NW == 4) ? 1 : 2) : 0;
-  static int mbar = -1;                    // CNB_ATTN_MBAR=0: block barrier per tile instead of the mbarrier ring
-  if (mbar < 0) {
-    const char* e = getenv("CNB_ATTN_MBAR");
-    mbar = e ? atoi(e) : 1;
-  }
-  if (HV != 0 && halves == 1 && mbar) return launch2<D, BK, NW, false, HV, (HV != 0)>(qkv, out, B, L, E, heads, st);
-  if (HV != 0 && halves == 1) return launch2<D, BK, NW, false, HV, false>(qkv, out, B, L, E, heads, st);
-  if (HV != 0 && halves == 2) return launch2<D, BK, NW, false, (HV != 0 ? 2 : 0), false>(qkv, out, B, L, E, heads, st);
-  if (HV != 0 && halves == 3) return launch2<D, BK, NW, false, (HV != 0 ? 1 : 0), false>(qkv, out, B, L, E, heads, st);
-  return launch2<D, BK, NW, false, 0, false>(qkv, out, B, L, E, heads, st);
+  if (HV != 0 && halves == 1) return launch2<D, BK, NW, false, HV>(qkv, out, B, L, E, heads, st);
+  if (HV != 0 && halves == 2) return launch2<D, BK, NW, false, (HV != 0 ? 2 : 0)>(qkv, out, B, L, E, heads, st);
+  if (HV != 0 && halves == 3) return launch2<D, BK, NW, false, (HV != 0 ? 1 : 0)>(qkv, out, B, L, E, heads, st);
+  return launch2<D, BK, NW, false, 0>(qkv, out, B, L, E, heads, st);
 }
 
 static inline long long padded(int L, int bq, int bk) {

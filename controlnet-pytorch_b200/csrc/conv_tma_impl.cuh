@@ -93,6 +93,9 @@ __device__ __forceinline__ void tma_store_2d(const void* map, uint32_t src, int 
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(x), "r"(y)
                : "memory");
 }
+__device__ __forceinline__ void prefetch_tensormap(const void* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -186,6 +189,15 @@ conv_tma_kernel(const __grid_constant__ TmaArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 0 && lane == 0) {                  // descriptor fetches overlap the previous kernel's tail (before pdl_wait)
+    prefetch_tensormap(&a.map_a);
+    prefetch_tensormap(&a.map_b);
+    if (a.kchunks2 > 0) prefetch_tensormap(&a.map_a2);
+  }
+  if (EPI == 6 && warp == 2 && lane == 0) {
+    prefetch_tensormap(&a.map_out);
+    if (a.residual) prefetch_tensormap(&a.map_res);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

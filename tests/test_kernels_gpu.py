@@ -280,6 +280,35 @@ def test_conv_k_concat_second_input(pk, B, C, Cx, Cout, H, W):
     assert rt.lib().cnb_tc_error_flag() == 0
 
 
+@pytest.mark.parametrize("kind,B,Cin,Cout,H,W", [("1x1", 3, 64, 16, 7, 7), ("1x1", 5, 64, 48, 7, 7), ("1x1", 2, 32, 64, 14, 14),
+                                                 ("1x1", 3, 64, 96, 7, 7), ("1x1", 2, 64, 192, 9, 5), ("1x1", 7, 256, 256, 7, 7),
+                                                 ("1x1", 3, 256, 768, 7, 7), ("3x3", 2, 128, 128, 7, 7), ("4x4s2", 2, 64, 64, 14, 14),
+                                                 ("1x1", 1, 24, 32, 5, 5), ("1x1", 150, 64, 64, 7, 7)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_conv_dense_f16_epilogue_offsets(pk, kind, B, Cin, Cout, H, W, with_res):
+    """Dense fp16-stream epilogue (per-warp staging + TMA store, fp16 residual fetched by TMA): every N-tile width, several
+    N tiles, ragged M (rows past the end clipped by the tensor map), output and residual at channel offsets of wider
+    buffers (the decoder's concat layout) - the neighbouring channels must stay untouched."""
+    ops, rt = pk
+    k = {"3x3": 3, "1x1": 1, "4x4s2": 4}[kind]
+    x, w, b = rnd(B, Cin, H, W, seed=1), rnd(Cout, Cin, k, k, seed=2) / math.sqrt(Cin * k * k), rnd(Cout, seed=3)
+    ref = _conv_ref(kind, x.half().float(), w.half().float(), b)
+    OH, OW = ref.shape[2], ref.shape[3]
+    res = rnd(B, Cout, OH, OW, seed=5).half()
+    want = ref + (res.float() if with_res else 0.0)
+    wp = ops.pack_conv_weight(w.cuda(), round_tf32=False)
+    lo, hi = 16, 8                                        # channels before / after the written window
+    out = torch.full((B, OH, OW, lo + Cout + hi), 7.0, device="cuda", dtype=torch.float16)
+    resbuf = torch.zeros((B, OH, OW, 8 + Cout), device="cuda", dtype=torch.float16)
+    resbuf[..., 8:] = nhwc(res.float()).cuda().half()
+    ops.conv(nhwc(x).cuda().half(), wp, kind, Cout, bias=b.cuda(), mode=rt.MODE_F16, weight_lp=ops.cast_f16(wp),
+             out=out, out_coff=lo, residual=resbuf if with_res else None, res_coff=8)
+    got = out[..., lo:lo + Cout].float().cpu()
+    assert rel_l2(nchw(got), want) < 6e-4
+    assert (out[..., :lo] == 7.0).all() and (out[..., lo + Cout:] == 7.0).all()
+    assert rt.lib().cnb_tc_error_flag() == 0
+
+
 def test_conv_out_reads_fp16(pk):
     """conv_out (Cout <= 4) on fp16 activations, as GroupNorm(norm_out) emits them in the tensor-core modes."""
     ops, rt = pk
