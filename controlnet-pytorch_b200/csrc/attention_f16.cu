@@ -79,11 +79,11 @@ __host__ __device__ constexpr int attn_sub(int D, int BK, int NW) { return (ATTN
 #ifndef ATTN_MIN_BLOCKS
 #define ATTN_MIN_BLOCKS 7
 #endif
-template <int D, int BK, int NW, bool H2, int HALVES>
+template <int D, int BK, int NW, bool H2, int VAR>
 #ifndef ATTN_MIN_BLOCKS8
 #define ATTN_MIN_BLOCKS8 3   // 8-warp kernels: <= 85 registers (d = 24: 122 -> 80, L = 1024 launch 2.15 -> 1.97 ms)
 #endif
-__global__ void __launch_bounds__(NW * 32, (NW == 4 && D <= 16) ? (HALVES == 2 ? 8 : ATTN_MIN_BLOCKS) : (NW == 8 ? (HALVES == 2 ? 4 : ATTN_MIN_BLOCKS8) : 0))
+__global__ void __launch_bounds__(NW * 32, (NW == 4 && D <= 16) ? ((VAR & 2) ? 8 : ATTN_MIN_BLOCKS) : (NW == 8 ? ((VAR & 2) ? 4 : ATTN_MIN_BLOCKS8) : 0))
 attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int L, int E, float scale_log2) {
   constexpr int d = D;
   constexpr int DP = (D + 15) / 16 * 16;         // K extent of Q K^T
@@ -94,8 +94,13 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
   constexpr int NT = BK / 8;                     // S column tiles
   constexpr int KS = DP / 16;                    // k-steps of Q K^T
   constexpr int THREADS = NW * 32;
-  constexpr int SUB = attn_sub(D, BK, NW);       // key tiles per block barrier
-  constexpr int NSLOT = 3 * SUB;                 // smem ring: three groups of SUB tiles
+  // VAR: bit 0 = 64-key tiles processed as two 32-key halves, bit 1 = 64-register build (8 CTAs of 4 warps per SM),
+  //      bit 2 = two tiles per block barrier from a ring of TWO groups (the next group is requested right after the
+  //      barrier that frees the other one; a group's compute time covers the L2 latency)
+  constexpr bool HALVES = (VAR & 1) != 0;
+  constexpr bool RING2 = (VAR & 4) != 0;
+  constexpr int SUB = RING2 ? 2 : attn_sub(D, BK, NW);   // key tiles per block barrier
+  constexpr int NSLOT = (RING2 ? 2 : 3) * SUB;           // smem ring: two / three groups of SUB tiles
   static_assert(BK % 16 == 0, "BK must be a multiple of 16");
   extern __shared__ __align__(16) __half smem[];   // [3 * SUB slots][K | V][BK][STRIDE]
   pdl_trigger();
@@ -311,20 +316,21 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
   const bool active = q0 < L;
   const int ngroups = (ntiles + SUB - 1) / SUB;
   load_group(0);
-  if (ngroups > 1) load_group(1);
+  if (!RING2 && ngroups > 1) load_group(1);
   const bool ragged = (L % BK) != 0;
   for (int grp = 0; grp < ngroups; ++grp) {
-    if (grp + 1 < ngroups) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    if (!RING2 && grp + 1 < ngroups) asm volatile("cp.async.wait_group 1;" ::: "memory");
     else asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    if (grp + 2 < ngroups) load_group(grp + 2);
+    if (RING2) { if (grp + 1 < ngroups) load_group(grp + 1); }
+    else if (grp + 2 < ngroups) load_group(grp + 2);
     if (active) {                                  // warps whose 16 query rows are all padding only help with the loads
 #pragma unroll
       for (int hh = 0; hh < SUB; ++hh) {
         const int t = grp * SUB + hh;
         if (t >= ntiles) break;
         using G0_ = std::integral_constant<int, 0>;
-        if constexpr (HALVES != 0 && BK == 64) {
+        if constexpr (HALVES && BK == 64) {
           // the tile in two 32-key halves (S of a half = 16 registers instead of 32): at 7 CTAs per SM (72 registers) the
           // compiler otherwise re-derives every lane-dependent address from %tid inside the tile loop - ~40 % of the
           // instructions of a tile were that bookkeeping (ncu: 7.4 issued instructions per exponential)
@@ -375,18 +381,18 @@ attention_f16_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, i
 
 static int g_h2 = -1;   // CNB_ATTN_EXP2H=1: ex2.approx.f16x2 exponentials (no faster on sm_100a: two MUFU ops per pair)
 
-template <int D, int BK, int NW, bool H2, int HALVES>
+template <int D, int BK, int NW, bool H2, int VAR>
 static int launch2(const void* qkv, void* out, int B, int L, int E, int heads, cudaStream_t st) {
   constexpr int DP = (D + 15) / 16 * 16;
-  constexpr size_t SMEM = (size_t)3 * attn_sub(D, BK, NW) * 2 * BK * (DP + 8) * sizeof(__half);
+  constexpr size_t SMEM = (size_t)((VAR & 4) ? 4 : 3 * attn_sub(D, BK, NW)) * 2 * BK * (DP + 8) * sizeof(__half);
   static DeviceOnce attr_once;
   if (attr_once.first()) {
-    CNB_CUDA(cudaFuncSetAttribute(attention_f16_kernel<D, BK, NW, H2, HALVES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CNB_CUDA(cudaFuncSetAttribute(attention_f16_kernel<D, BK, NW, H2, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)SMEM));
   }
   const float scale_log2 = 1.4426950408889634f / sqrtf((float)D);
   dim3 grid(ceil_div(L, 16 * NW), heads, B);
-  CNB_CUDA(launch_pdl((long long)B * L * E, attention_f16_kernel<D, BK, NW, H2, HALVES>, grid, dim3(NW * 32), SMEM, st,
+  CNB_CUDA(launch_pdl((long long)B * L * E, attention_f16_kernel<D, BK, NW, H2, VAR>, grid, dim3(NW * 32), SMEM, st,
                       reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(out), L, E, scale_log2));
   CNB_LAUNCH_CHECK();
   return CNB_OK;
@@ -406,10 +412,12 @@ static int launch(const void* qkv, void* out, int B, int L, int E, int heads, cu
   if (D <= 32 && g_h2) return launch2<D, BK, NW, (D <= 32), 0>(qkv, out, B, L, E, heads, st);
   // measured (profiles/r02_attention_table.md): halves pay everywhere at head dims <= 16; with them the kernel also fits
   // 64 registers = 8 CTAs (4 warps) / 4 CTAs (8 warps) per SM, which wins or ties except at d = 16 with 4 warps (spills)
-  constexpr int HV = (BK == 64 && D <= 16) ? ((D == 16 && NW == 4) ? 1 : 2) : 0;
-  if (HV != 0 && halves == 1) return launch2<D, BK, NW, false, HV>(qkv, out, B, L, E, heads, st);
-  if (HV != 0 && halves == 2) return launch2<D, BK, NW, false, (HV != 0 ? 2 : 0)>(qkv, out, B, L, E, heads, st);
-  if (HV != 0 && halves == 3) return launch2<D, BK, NW, false, (HV != 0 ? 1 : 0)>(qkv, out, B, L, E, heads, st);
+  constexpr bool NARROW = BK == 64 && D <= 16;
+  // halves, + the 64-register build where it does not spill, + two tiles per barrier for the 8-warp CTAs (measured:
+  // L = 1024 d = 16 1362 -> 1311 us, L = 196 d = 16 88 -> 82 us; the 4-warp CTAs lose: L = 784 d = 16 854 -> 877 us)
+  constexpr int HV = NARROW ? (((D == 16 && NW == 4) ? 1 : 3) | (NW == 8 ? 4 : 0)) : 0;
+  if (NARROW && halves == 1) return launch2<D, BK, NW, false, HV>(qkv, out, B, L, E, heads, st);
+  if (NARROW && halves == 2) return launch2<D, BK, NW, false, NARROW ? (HV | 4) : 0>(qkv, out, B, L, E, heads, st);
   return launch2<D, BK, NW, false, 0>(qkv, out, B, L, E, heads, st);
 }
 

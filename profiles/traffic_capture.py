@@ -1,12 +1,12 @@
 """GPU box, under ncu:  DRAM bytes per launch for every (kernel family, layer shape) of one eager denoising step.
 
-    ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:cnb --csv \\
+    ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \\
         --log-file gpurun_out/traffic.csv python profiles/traffic_capture.py [batch]
     python profiles/traffic_capture.py --merge gpurun_out/traffic.csv gpurun_out/traffic_labels.json   (no GPU)
 
 The first form runs bench.kernel_breakdown (which notes the process-wide ordinal of every libcnb200 launch it times) and
-writes the labels; the second joins them with ncu's per-launch rows (same order: ncu lists the process's cnb:: kernels
-in launch order) into profiles/ncu_traffic.json = {"family|shape|batch": bytes per launch}, which bench.py reports as
+writes the labels; the second joins them with ncu's per-launch rows (same order: ncu lists the process's kernels in
+launch order; rows of kernels outside the library's namespaces - torch's own - are dropped first) into profiles/ncu_traffic.json = {"family|shape|batch": bytes per launch}, which bench.py reports as
 `roofline.traffic`."""
 import collections
 import csv
@@ -42,7 +42,10 @@ def merge(csv_path, labels_path):
             continue
         rows.append(dict(zip(hdr, r)))
     per_launch = collections.OrderedDict()          # ncu ID -> bytes (read + write)
+    ours = ("cnb::", "tma::", "af16::", "atm::", "gnb::")
     for d in rows:
+        if not any(ns in d.get("Kernel Name", "") for ns in ours):
+            continue
         try:
             v = float(d["Metric Value"].replace(",", ""))
         except (KeyError, ValueError):
