@@ -170,6 +170,11 @@ def kernel_breakdown(model, sched, x, hint, n_steps=2):
         smp.sample_eager(x, hint, steps=1)          # warm caches
         rec.clear()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # the eager step is enqueued BEHIND a spinning kernel, so that every (event, launch, event) triple is already in
+        # the stream when the GPU reaches it: the per-launch times are device time, not the host's launch gaps (which at
+        # small per-rank batches, with N processes sharing the host, were longer than the kernels)
+        torch.cuda.synchronize()
+        torch.cuda._sleep(int(3e8))
         t0.record()
         smp.sample_eager(x, hint, steps=n_steps)
         t1.record()
