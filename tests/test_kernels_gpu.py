@@ -298,7 +298,8 @@ def test_conv_dense_f16_epilogue_offsets(pk, kind, B, Cin, Cout, H, W, with_res)
     want = ref + (res.float() if with_res else 0.0)
     wp = ops.pack_conv_weight(w.cuda(), round_tf32=False)
     lo, hi = 16, 8                                        # channels before / after the written window
-    out = torch.full((B, OH, OW, lo + Cout + hi), 7.0, device="cuda", dtype=torch.float16)
+    big = torch.full((B + 1, OH, OW, lo + Cout + hi), 7.0, device="cuda", dtype=torch.float16)
+    out = big[:B]                                         # one guard sample behind the last row the kernel may touch
     resbuf = torch.zeros((B, OH, OW, 8 + Cout), device="cuda", dtype=torch.float16)
     resbuf[..., 8:] = nhwc(res.float()).cuda().half()
     ops.conv(nhwc(x).cuda().half(), wp, kind, Cout, bias=b.cuda(), mode=rt.MODE_F16, weight_lp=ops.cast_f16(wp),
@@ -306,6 +307,7 @@ def test_conv_dense_f16_epilogue_offsets(pk, kind, B, Cin, Cout, H, W, with_res)
     got = out[..., lo:lo + Cout].float().cpu()
     assert rel_l2(nchw(got), want) < 6e-4
     assert (out[..., :lo] == 7.0).all() and (out[..., lo + Cout:] == 7.0).all()
+    assert (big[B] == 7.0).all()                          # rows past M are clipped, not written
     assert rt.lib().cnb_tc_error_flag() == 0
 
 
