@@ -282,6 +282,9 @@ def make_roofline(fams, step_ms, batch):
         f = fams[fam_]
         lines = [shape_line(fam_, s_, v_) for s_, v_ in sorted(f["shapes"].items(), key=lambda kv: -kv[1]["ms"])]
         big = [l_ for l_ in lines if l_["share_of_step"] >= 0.02] or lines[:1]
+        if os.environ.get("CNB_BENCH_SHAPES"):               # full per-shape table, one JSON line per family
+            with open(os.environ["CNB_BENCH_SHAPES"], "a") as fh:
+                fh.write(json.dumps({"family": fam_, "batch": batch, "shapes": lines}) + "\n")
         s_ = f["ms"] * 1e-3
         if fam_ == "groupnorm":
             tw = {"achieved": round(f["bytes"] / s_ / 1e9, 1), "peak": pk["hbm"], "unit": "GB/s",

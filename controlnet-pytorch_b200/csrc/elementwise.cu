@@ -273,6 +273,35 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, int ldi, int in_c
   dst[i] = (float)src[(b * HW + pix) * ldi + in_coff + c];
 }
 
+// EDM pre-conditioning fused with the layout change (consistency_controlnet_distilled.py:92 and :132): the scaled input
+// c_in[b] * x goes straight to the channels-last workspace, and the student's output c_skip[b] * x + c_out[b] * F is
+// formed while F leaves it.  Same fp32 operations in the same order as the separate launches (mul; mul, mul, add - no
+// FMA contraction), so the results are bit-identical to scale_rows + the plain layout kernels.
+__global__ void scale_nchw_to_nhwc_kernel(const float* __restrict__ a, const float* __restrict__ src,
+                                          float* __restrict__ dst, int C, int HW, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // index over (b, p, c): c fastest
+  if (i >= total) return;
+  int c = (int)(i % C);
+  long long bp = i / C;
+  int pix = (int)(bp % HW);
+  long long b = bp / HW;
+  dst[i] = __fmul_rn(a[b], src[(b * C + c) * HW + pix]);
+}
+
+template <typename T>
+__global__ void edm_combine_to_nchw_kernel(const float* __restrict__ cskip, const float* __restrict__ x,
+                                           const float* __restrict__ cout, const T* __restrict__ f, int ldi, int in_coff,
+                                           float* __restrict__ dst, int C, int HW, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // index over (b, c, p): p fastest
+  if (i >= total) return;
+  int pix = (int)(i % HW);
+  long long bc = i / HW;
+  int c = (int)(bc % C);
+  long long b = bc / C;
+  const float fv = (float)f[(b * HW + pix) * ldi + in_coff + c];
+  dst[i] = __fadd_rn(__fmul_rn(cskip[b], x[i]), __fmul_rn(cout[b], fv));
+}
+
 template <typename T>
 __global__ void copy_channels_kernel(const T* __restrict__ src, int lds, int s_coff, T* __restrict__ dst,
                                      int ldd, int d_coff, int C, long long total) {
@@ -440,6 +469,29 @@ extern "C" int cnb_nchw_to_nhwc(const float* src, float* dst, int B, int C, int 
   long long total = (long long)B * C * HW;
   CNB_REQUIRE(total > 0 && ldo >= out_coff + C, "nchw_to_nhwc: bad dims");
   nchw_to_nhwc_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)s>>>(src, dst, C, HW, ldo, out_coff, total);
+  CNB_LAUNCH_CHECK();
+  return CNB_OK;
+}
+
+extern "C" int cnb_scale_nchw_to_nhwc(const float* a, const float* src, float* dst, int B, int C, int HW,
+                                      cnb_stream_t s) {
+  long long total = (long long)B * C * HW;
+  CNB_REQUIRE(a && src && dst && total > 0, "scale_nchw_to_nhwc: bad args");
+  scale_nchw_to_nhwc_kernel<<<blocks_for(total, 256), 256, 0, (cudaStream_t)s>>>(a, src, dst, C, HW, total);
+  CNB_LAUNCH_CHECK();
+  return CNB_OK;
+}
+
+extern "C" int cnb_edm_combine_to_nchw(const float* c_skip, const float* x, const float* c_out, const void* f, int ldi,
+                                       int in_coff, float* dst, int B, int C, int HW, int f_f16, cnb_stream_t s) {
+  long long total = (long long)B * C * HW;
+  CNB_REQUIRE(c_skip && x && c_out && f && dst && total > 0 && ldi >= in_coff + C, "edm_combine_to_nchw: bad args");
+  if (f_f16)
+    edm_combine_to_nchw_kernel<__half><<<blocks_for(total, 256), 256, 0, (cudaStream_t)s>>>(
+        c_skip, x, c_out, reinterpret_cast<const __half*>(f), ldi, in_coff, dst, C, HW, total);
+  else
+    edm_combine_to_nchw_kernel<float><<<blocks_for(total, 256), 256, 0, (cudaStream_t)s>>>(
+        c_skip, x, c_out, reinterpret_cast<const float*>(f), ldi, in_coff, dst, C, HW, total);
   CNB_LAUNCH_CHECK();
   return CNB_OK;
 }

@@ -30,9 +30,9 @@ def set_branch_parallel(value):
     _FORCE[0] = value
 
 
-def _side_stream(dev):
+def _side_stream(dev, which=0):
     import torch
-    key = (str(dev), torch.cuda.current_stream(dev).cuda_stream)
+    key = (str(dev), torch.cuda.current_stream(dev).cuda_stream, which)
     if key not in _SIDE:
         _SIDE[key] = torch.cuda.Stream(device=dev)
     return _SIDE[key]
@@ -47,65 +47,136 @@ def controlnet_forward(trained, control, down_zero, mid_zero, hint_feat_fn, x, t
     dev = x.device
     xn = ops.nchw_to_nhwc(x)
     t = E.check_t(t, x.shape[0], dev)
-
-    plan_t = E.temb_plan(trained, E.unet_time(trained, t, dev))
-    plan_c = E.temb_plan(control, E.unet_time(control, t, dev), with_ups=False)
     hf = hint_feat_fn(hint, mode)
+    nmid = len(control.mids)
 
-    def control_encoder():
-        """control.conv_in(x) + hint feature -> downs -> mids; returns the inputs of the zero convs."""
+    def skip_sums(cs, t_skips):
+        """zero_conv_i(control skip) + trained skip, written into the second half of the decoder's concat buffers
+        (controlnet.py:190-192, 216-218)."""
+        cats = []
+        for i, c in enumerate(cs):
+            B, H, W, C = c.shape
+            zc = down_zero[i]
+            cat = ops.empty(B, H, W, 2 * C, device=dev, dtype=c.dtype)
+            E.conv16(c, zc.weight, "1x1", C, mode, bias=E.raw(zc.bias), residual=t_skips[i], out=cat, out_coff=C)
+            cats.append(cat)
+        return cats
+
+    def inject(i, a, cm):
+        """a + mid_zero_conv_i(control mid output): the sum rides in the zero conv's epilogue (:207)."""
+        zc = mid_zero[i]
+        return E.conv16(cm, zc.weight, "1x1", zc.out_channels, mode, bias=E.raw(zc.bias), residual=a)
+
+    # The dependency graph of the reference's forward is wider than its statement order: the frozen encoder AND
+    # trained.mids[0] never read a control tensor; trained.mids[i] needs control.mids[i-1] only through mid zero conv
+    # i-1; the skip sums need the two encoders but nothing needs them before the decoder.  Under CUDA-graph capture the
+    # forward is therefore laid out on four streams (forked / joined with events = parallel graph branches):
+    #     cur  : trained conv_in -> downs -> mids[0] -> wait(control mid 0) inject -> mids[1] -> wait(...) inject -> ups
+    #     side : control t-embedding -> conv_in + hint -> downs -> mids[0] -> mids[1]
+    #     skip : trained t-embedding rows; later wait(both encoders) -> the skip sums
+    #     aux  : control t-embedding rows
+    # The critical path loses one mid block per mid level and the skip sums (round 2: B = 128 step 2.43 -> see DESIGN 5);
+    # the kernels of one branch fill the pipes the other leaves idle (MUFU-bound attention next to tensor- / HBM-bound
+    # convolutions and GroupNorms).  Same kernels, same inputs, same order per tensor: results are bit-identical to the
+    # sequential schedule.  CNB_BRANCH_PARALLEL=0 turns it off; CNB_BRANCH_PARALLEL=2 is the round-1 layout (control
+    # encoder + all its mids on the side stream, everything else after the join).
+    # Only under graph capture: in eager mode the extra stream bookkeeping (event waits, record_stream on every
+    # hand-over tensor) is host time, which is what a small-batch eager loop is bound by (CelebHQ B = 16: 6.9 -> 19.7 ms).
+    env = os.environ.get("CNB_BRANCH_PARALLEL", "1")
+    parallel = (env != "0") if _FORCE[0] is None else bool(_FORCE[0])
+    parallel = parallel and torch.cuda.is_current_stream_capturing()
+    early_mid = parallel and env != "2"
+
+    if not parallel:
+        plan_t = E.temb_plan(trained, E.unet_time(trained, t, dev))
+        plan_c = E.temb_plan(control, E.unet_time(control, t, dev), with_ups=False)
+        a = E.conv_in(trained, xn, mode)
+        t_skips = []
+        for d in trained.downs:
+            t_skips.append(a)
+            a = E.run_down(d, a, plan_t[d], mode)
         c = E.conv_in(control, xn, mode, residual=hf)
-        cs, cms = [], []
+        cs = []
         for d in control.downs:
             cs.append(c)
             c = E.run_down(d, c, plan_c[d], mode)
+        cms = []
         for mblk in control.mids:
             c = E.run_mid(mblk, c, plan_c[mblk], mode)
             cms.append(c)
-        return cs, cms
-
-    # The frozen encoder and the control encoder only meet at the zero convs, so they run on two streams (forked and
-    # joined with events; under CUDA-graph capture these become parallel graph branches): the kernels of one branch fill
-    # the pipes the other leaves idle -- MUFU-bound attention next to tensor- / HBM-bound convolutions and GroupNorms.
-    # Measured (MNIST, graph replay): B = 64 2.25 -> 1.95 ms, B = 256 4.15 -> 3.90 ms, B = 1024 13.00 -> 12.61 ms per step;
-    # results are bit-identical (same kernels, same order per tensor).  CNB_BRANCH_PARALLEL=0 turns it off.
-    # Only under graph capture: in eager mode the extra stream bookkeeping (event waits, record_stream on every
-    # hand-over tensor) is host time, which is what a small-batch eager loop is bound by (CelebHQ B = 16: 6.9 -> 19.7 ms).
-    parallel = os.environ.get("CNB_BRANCH_PARALLEL", "1") == "1" if _FORCE[0] is None else bool(_FORCE[0])
-    parallel = parallel and torch.cuda.is_current_stream_capturing()
-    if parallel:
+        cats = skip_sums(cs, t_skips)
+        for i in range(nmid):
+            a = inject(i, E.run_mid(trained.mids[i], a, plan_t[trained.mids[i]], mode), cms[i])
+    else:
         cur = torch.cuda.current_stream(dev)
-        side = _side_stream(dev)
+        side = _side_stream(dev, 0)
+        skip = _side_stream(dev, 1)
+        E.prewarm_conv_in(trained, xn, mode)       # the padded fp16 copy both conv_in layers read: before the fork
+        if early_mid:
+            # the two t-embedding chains (4 small launches each) leave the critical paths as well: they are only needed
+            # by the first resnet's conv1 epilogue, after conv_in and a GroupNorm
+            aux = _side_stream(dev, 2)
+            skip.wait_stream(cur)
+            aux.wait_stream(cur)
+            with torch.cuda.stream(skip):
+                plan_t = E.temb_plan(trained, E.unet_time(trained, t, dev))
+                ev_pt = skip.record_event()
+            with torch.cuda.stream(aux):
+                plan_c = E.temb_plan(control, E.unet_time(control, t, dev), with_ups=False)
+                ev_pc = aux.record_event()
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            cs, cms = control_encoder()
-    # frozen encoder
-    a = E.conv_in(trained, xn, mode)
-    t_skips = []
-    for d in trained.downs:
-        t_skips.append(a)
-        a = E.run_down(d, a, plan_t[d], mode)
-    if parallel:
-        cur.wait_stream(side)
-        for tns in cs + cms:
-            tns.record_stream(cur)
-    else:
-        cs, cms = control_encoder()
-
-    # skip sums land directly in the concat buffers of the decoder (controlnet.py:190-192, 216-218)
-    cats = []
-    for i, c in enumerate(cs):
-        B, H, W, C = c.shape
-        zc = down_zero[i]
-        cat = ops.empty(B, H, W, 2 * C, device=dev, dtype=c.dtype)
-        E.conv16(c, zc.weight, "1x1", C, mode, bias=E.raw(zc.bias), residual=t_skips[i], out=cat, out_coff=C)
-        cats.append(cat)
-
-    # mids: a = trained.mid(a) + mid_zero_conv(control.mid output)   (injection fused in the epilogue, :207)
-    for i in range(len(control.mids)):
-        a = E.run_mid(trained.mids[i], a, plan_t[trained.mids[i]], mode)
-        zc = mid_zero[i]
-        a = E.conv16(cms[i], zc.weight, "1x1", zc.out_channels, mode, bias=E.raw(zc.bias), residual=a)
+            if early_mid:
+                c = E.conv_in(control, xn, mode, residual=hf)
+                side.wait_event(ev_pc)
+                next(iter(plan_c.values())).table.record_stream(side)
+            else:
+                plan_c = E.temb_plan(control, E.unet_time(control, t, dev), with_ups=False)
+                c = E.conv_in(control, xn, mode, residual=hf)
+            cs, cms, ev_mid = [], [], []
+            for d in control.downs:
+                cs.append(c)
+                c = E.run_down(d, c, plan_c[d], mode)
+            ev_enc = side.record_event()
+            for mblk in control.mids:
+                c = E.run_mid(mblk, c, plan_c[mblk], mode)
+                cms.append(c)
+                ev_mid.append(side.record_event())
+        if early_mid:
+            a = E.conv_in(trained, xn, mode)
+            cur.wait_event(ev_pt)
+            next(iter(plan_t.values())).table.record_stream(cur)
+        else:
+            plan_t = E.temb_plan(trained, E.unet_time(trained, t, dev))
+            a = E.conv_in(trained, xn, mode)
+        t_skips = []
+        for d in trained.downs:
+            t_skips.append(a)
+            a = E.run_down(d, a, plan_t[d], mode)
+        if early_mid:
+            skip.wait_stream(cur)                  # trained skips
+            skip.wait_event(ev_enc)                # control skips
+            with torch.cuda.stream(skip):
+                for tns in cs + t_skips:
+                    tns.record_stream(skip)
+                cats = skip_sums(cs, t_skips)
+            for i in range(nmid):
+                a = E.run_mid(trained.mids[i], a, plan_t[trained.mids[i]], mode)
+                cur.wait_event(ev_mid[i])
+                cms[i].record_stream(cur)
+                a = inject(i, a, cms[i])
+            cur.wait_stream(side)
+            cur.wait_stream(skip)
+            cur.wait_stream(aux)
+            for tns in cats:
+                tns.record_stream(cur)
+        else:
+            cur.wait_stream(side)
+            for tns in cs + cms:
+                tns.record_stream(cur)
+            cats = skip_sums(cs, t_skips)
+            for i in range(nmid):
+                a = inject(i, E.run_mid(trained.mids[i], a, plan_t[trained.mids[i]], mode), cms[i])
 
     for u in trained.ups:
         a = E.run_up(u, a, None, plan_t[u], mode, cat=cats.pop())

@@ -413,6 +413,17 @@ def conv_in(unet, x_nhwc, mode, residual=None):
     return conv3x3_narrow_in(unet.conv_in, x_nhwc, mode, residual=residual)
 
 
+def prewarm_conv_in(unet, x_nhwc, mode):
+    """Build the memoised padded fp16 copy of x (pad16_f16) on the CURRENT stream when conv_in will take the tensor-core
+    route.  The ControlNet forward calls this before it forks its branches: both conv_in layers read that one buffer,
+    and whichever branch created it first would otherwise hand it to the other stream without an ordering edge."""
+    conv = unet.conv_in
+    cin, cout = conv.in_channels, conv.out_channels
+    if (_WIDE_IN and mode != rt.MODE_F32 and _F16_ENABLED and cin <= 8 and cout >= 64 and cout % 16 == 0 and
+            x_nhwc.dtype == torch.float32):
+        pad16_f16(x_nhwc)
+
+
 def gn_silu_conv_tail(norm, conv, h, mode):
     """GroupNorm -> SiLU -> 3x3 conv to a handful of channels (U-Net conv_out, VAE decoder / encoder conv_out).
     Returns the NHWC result, possibly as a channel-narrowed VIEW of a wider buffer (ops.nhwc_to_nchw reads strides).

@@ -76,10 +76,10 @@ class ConsistencyControlNet(nn.Module):
         if not getattr(self, "_skip_boundary_sync", False) and int(flag.item()):
             return x_t                # host sync, exactly like the reference's `if torch.all(...)` (:81-82)
         mode = rt.get_mode()
-        x_scaled = ops.scale_rows(coef[0], x_t)                       # c_in * x_t
-        f_theta = student_body(self, ops.nchw_to_nhwc(x_scaled), t_index, hint, mode)
-        f_theta = ops.nhwc_to_nchw(f_theta)
-        return ops.scale_rows(coef[1], x_t, coef[2], f_theta)         # c_skip * x_t + c_out * F
+        # c_in * x_t on the way into the channels-last workspace, c_skip * x_t + c_out * F on the way out: one launch
+        # each (round 1 ran scale_rows -> nchw_to_nhwc -> body -> nhwc_to_nchw -> scale_rows), bit-identical
+        f_theta = student_body(self, ops.scale_nchw_to_nhwc(coef[0], x_t), t_index, hint, mode)
+        return ops.edm_combine_to_nchw(coef[1], x_t, coef[2], f_theta)
 
 
 class ConsistencyControlNetDistilled(nn.Module):

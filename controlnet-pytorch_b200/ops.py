@@ -259,6 +259,33 @@ def x0_from_eps(xt, eps, sqrt_one_minus, sqrt_alpha, t):
     return out
 
 
+def scale_nchw_to_nhwc(a, x):
+    """a[b] * x, NCHW fp32 -> channels-last fp32 in one launch (EDM c_in scaling on the way into conv_in)."""
+    rt.require_cuda(a, x)
+    B, C, H, W = x.shape
+    out = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32)
+    rt.check(rt.lib().cnb_scale_nchw_to_nhwc(a.data_ptr(), x.data_ptr(), out.data_ptr(), B, C, H * W, rt.stream()))
+    return out
+
+
+def edm_combine_to_nchw(c_skip, x, c_out, f, in_coff=0, c=None):
+    """c_skip[b] * x + c_out[b] * f with f leaving the channels-last workspace (fp32 / fp16, possibly a channel-narrowed
+    view): the student's output in NCHW fp32, one launch."""
+    rt.require_cuda(c_skip, x, c_out, f)
+    B, H, W, cv = f.shape
+    ld = f.stride(2)
+    if f.stride(3) != 1 or f.stride(1) != W * ld or f.stride(0) != H * W * ld or ld < cv:
+        raise rt.CnbError("edm_combine_to_nchw: expected a channels-last tensor or a channel slice of one")
+    c = cv - in_coff if c is None else c
+    if tuple(x.shape) != (B, c, H, W) or x.dtype != torch.float32 or not x.is_contiguous():
+        raise rt.CnbError("edm_combine_to_nchw: x must be the contiguous fp32 NCHW tensor matching f")
+    out = torch.empty_like(x)
+    rt.check(rt.lib().cnb_edm_combine_to_nchw(c_skip.data_ptr(), x.data_ptr(), c_out.data_ptr(), f.data_ptr(), ld,
+                                              in_coff, out.data_ptr(), B, c, H * W,
+                                              1 if f.dtype == torch.float16 else 0, rt.stream()))
+    return out
+
+
 def scale_rows(a, x, c=None, y=None):
     rt.require_cuda(a, x, c, y)
     out = torch.empty_like(x)

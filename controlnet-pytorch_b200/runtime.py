@@ -68,6 +68,9 @@ _SIGS = {
     "cnb_scale_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_void_p]),
     "cnb_x0_from_eps": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_ll,
                                 c_void_p]),
+    "cnb_scale_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "cnb_edm_combine_to_nchw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
+                                        c_int, c_int, c_void_p]),
     "cnb_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "cnb_nhwc_to_nchw": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "cnb_copy_channels": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_ll, c_int, c_int, c_void_p]),

@@ -186,6 +186,13 @@ int cnb_edm_coeffs(const float* sigma, int B, float sigma_data, float sigma_min,
 /* out[b, i] = a[b] * x[b, i] (+ c[b] * y[b, i] if y != NULL); per-sample scalars (consistency :92, :132). */
 int cnb_scale_rows(const float* a, const float* x, const float* c, const float* y, float* out, int B,
                    long long per_sample, cnb_stream_t stream);
+/* The same two expressions fused with the layout change around the student body (:92 -> conv_in, conv_out -> :132):
+ * dst (NHWC fp32) = a[b] * src (NCHW fp32);   dst (NCHW fp32) = c_skip[b] * x (NCHW fp32) + c_out[b] * f, f the
+ * channels-last body output (fp32 or fp16, leading dimension ldi, channel offset in_coff).  Bit-identical to
+ * cnb_scale_rows composed with cnb_nchw_to_nhwc / cnb_nhwc_to_nchw. */
+int cnb_scale_nchw_to_nhwc(const float* a, const float* src, float* dst, int B, int C, int HW, cnb_stream_t stream);
+int cnb_edm_combine_to_nchw(const float* c_skip, const float* x, const float* c_out, const void* f, int ldi, int in_coff,
+                            float* dst, int B, int C, int HW, int f_f16, cnb_stream_t stream);
 /* Teacher-side x0 from a noise prediction with per-sample timesteps (distribution_matching_controlnet.py:191-216,
  * consistency_controlnet_distilled.py:201-228): out = clamp((xt - sqrt_one_minus[t_b] * eps) / sqrt_alpha[t_b], -1, 1);
  * t holds t_count in {1, B} int64 indices < num_timesteps into the two scheduler tables (device fp32). */

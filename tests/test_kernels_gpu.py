@@ -398,6 +398,17 @@ def test_layout_and_scale(pk):
     got = ops.scale_rows(a.cuda(), x.cuda(), c.cuda(), y.cuda())
     want = a[:, None, None, None] * x + c[:, None, None, None] * y
     assert torch.equal(got.cpu(), want)
+    # EDM pre-conditioning fused with the layout change (consistency_controlnet_distilled.py:92, :132): bit-identical to
+    # the reference's fp32 expressions, for fp32 and fp16 body outputs and for a channel-narrowed view of a wider buffer
+    assert torch.equal(ops.scale_nchw_to_nhwc(a.cuda(), x.cuda()).cpu(), nhwc(a[:, None, None, None] * x))
+    f = nhwc(y).cuda()
+    assert torch.equal(ops.edm_combine_to_nchw(a.cuda(), x.cuda(), c.cuda(), f).cpu(), want)
+    f16 = f.half()
+    want16 = a[:, None, None, None] * x + c[:, None, None, None] * f16.float().cpu().permute(0, 3, 1, 2)
+    assert torch.equal(ops.edm_combine_to_nchw(a.cuda(), x.cuda(), c.cuda(), f16).cpu(), want16)
+    wide = torch.zeros(3, 6, 7, 16, device="cuda", dtype=torch.float16)
+    wide[..., :5] = f16
+    assert torch.equal(ops.edm_combine_to_nchw(a.cuda(), x.cuda(), c.cuda(), wide[..., :5]).cpu(), want16)
 
 
 def test_no_cpu_fallback(pk):
