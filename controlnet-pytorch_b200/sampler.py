@@ -85,12 +85,11 @@ class DDPMSampler:
         # tensor- / HBM-bound convolutions and GroupNorms of the other (measured at B = 1024: 13.08 -> 12.65 ms).
         B = self.xt.shape[0]
         per = self.xt[0].numel()
-        # Default: off for the MNIST / CIFAR widths, where the ControlNet forward's own two-stream fork of its encoders
-        # (models/_controlnet_common.py) gives the same overlap without halving the per-kernel batch (B = 1024: 12.59
-        # split vs 12.61 branches vs 12.70 ms both); on for the 190 M-parameter CelebHQ model from B = 128, where the
-        # split measured better (B = 256: 31.2 unsplit, 31.1 branches, 30.5 ms split).  Never both.
-        big_model = sum(p.numel() for p in self.model.parameters()) > 50_000_000
-        nsplit = int(os.environ.get("CNB_SAMPLER_SPLIT", "2" if (big_model and B >= 128) else "1"))
+        # Default: off.  The ControlNet forward's own fork of its branches (models/_controlnet_common.py) gives the overlap
+        # without halving the per-kernel batch: MNIST B = 1024 12.59 split vs 12.61 two branches vs 11.84 ms with the
+        # four-stream layout; CelebHQ (190 M parameters) B = 256: 31.2 unsplit, 31.1 two branches, 28.25 split, 27.79 ms
+        # four streams (gpu_jobs/r2_34_cfg3.sh).  CNB_SAMPLER_SPLIT=2 keeps the split available.  Never both.
+        nsplit = int(os.environ.get("CNB_SAMPLER_SPLIT", "1"))
         nsplit = max(1, min(nsplit, B))
         bounds = [shard_bounds(B, nsplit, k) for k in range(nsplit)]
         self._bounds = bounds

@@ -401,6 +401,34 @@ def test_split_stream_sampler_is_bit_identical(rt, monkeypatch):
     assert rt.lib().cnb_tc_error_flag() == 0
 
 
+def test_branch_layouts_of_the_step_graph_are_bit_identical(rt, monkeypatch):
+    """models/_controlnet_common.py lays the ControlNet forward out on four capture streams (trained mids ahead of the
+    control join, skip sums and t-embedding rows off the critical path).  Every layout - sequential (0), four streams
+    (1, default), the round-1 two-stream fork (2) - runs the same kernels on the same inputs, so the replayed samples
+    must equal the eager loop bit for bit: MNIST DDPM ControlNet, the tiny LDM ControlNet (image-pyramid hints), and a
+    CIFAR-width ControlNet whose conv_in layers share the padded fp16 copy of x (built before the fork)."""
+    rt.set_mode("f16" if rt.lib().cnb_has_tcgen05() else "fp32")
+    S = _mod("sampler")
+    L = _mod("scheduler.linear_noise_scheduler").LinearNoiseScheduler
+    cases = [
+        ("mnist", _fill(_mod("models.controlnet").ControlNet(syn.MNIST_PARAMS)), L(**syn.MNIST_DIFFUSION),
+         inputs("branch_mnist", 6, 1, 28)),
+        ("tiny_ldm", _fill(_mod("models.controlnet_ldm").ControlNet(4, syn.TINY_LDM_PARAMS, down_sample_factor=8)),
+         L(ldm_scheduler=True, **syn.CELEBHQ_DIFFUSION), inputs("branch_ldm", 3, 4, 8, hint_size=64, p=0.05)),
+        ("cifar", _fill(_mod("models.controlnet").ControlNet(syn.CIFAR_PARAMS)), L(**syn.MNIST_DIFFUSION),
+         inputs("branch_cifar", 3, 3, 32)),
+    ]
+    for name, m, sched, (x, hint) in cases:
+        xc, hc = x.cuda(), hint.cuda()
+        eager = S.DDPMSampler(m, sched, seed=11, use_graph=False).sample(xc, hc, steps=3, elem_offset=64)
+        for layout in ("0", "1", "2"):
+            monkeypatch.setenv("CNB_BRANCH_PARALLEL", layout)
+            got = S.DDPMSampler(m, sched, seed=11, use_graph=True).sample(xc, hc, steps=3, elem_offset=64)
+            assert torch.equal(got[0], eager[0]) and torch.equal(got[1], eager[1]), (name, layout)
+            assert torch.isfinite(got[0]).all()
+    assert rt.lib().cnb_tc_error_flag() == 0
+
+
 def test_dropin_shim_runs_the_reference_tool_loop(rt, tmp_path):
     """the reference tool's import lines and sampling loop (tools/sample_ddpm_controlnet.py
     :9-12, :43-51), run in a fresh interpreter with controlnet-pytorch_b200/dropin first on sys.path, execute on the
