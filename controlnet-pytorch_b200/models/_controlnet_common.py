@@ -20,26 +20,16 @@ def split_prefix(state, prefix, exclude=()):
             if k.startswith(prefix) and not any(k.startswith(e) for e in exclude)}
 
 
-_SIDE = {}
-_FORCE = [None]          # sampler override: True / False / None (= environment default)
-
-
 def set_branch_parallel(value):
     """Override CNB_BRANCH_PARALLEL for the calls that follow (None restores the default); used by the sampler when it
-    already runs batch halves on parallel streams."""
-    _FORCE[0] = value
+    already runs batch parts on parallel streams."""
+    E._FORCE_PAR[0] = value
 
 
-def _side_stream(dev, which=0):
-    import torch
-    key = (str(dev), torch.cuda.current_stream(dev).cuda_stream, which)
-    if key not in _SIDE:
-        _SIDE[key] = torch.cuda.Stream(device=dev)
-    return _SIDE[key]
+_side_stream = E.side_stream
 
 
 def controlnet_forward(trained, control, down_zero, mid_zero, hint_feat_fn, x, t, hint):
-    import os
     import torch
     x = E._check_x(x)
     hint = E._check_x(hint)
@@ -82,10 +72,9 @@ def controlnet_forward(trained, control, down_zero, mid_zero, hint_feat_fn, x, t
     # encoder + all its mids on the side stream, everything else after the join).
     # Only under graph capture: in eager mode the extra stream bookkeeping (event waits, record_stream on every
     # hand-over tensor) is host time, which is what a small-batch eager loop is bound by (CelebHQ B = 16: 6.9 -> 19.7 ms).
-    env = os.environ.get("CNB_BRANCH_PARALLEL", "1")
-    parallel = (env != "0") if _FORCE[0] is None else bool(_FORCE[0])
-    parallel = parallel and torch.cuda.is_current_stream_capturing()
-    early_mid = parallel and env != "2"
+    layout = E.capture_parallel()
+    parallel = layout != "0"
+    early_mid = layout == "1"
 
     if not parallel:
         plan_t = E.temb_plan(trained, E.unet_time(trained, t, dev))

@@ -294,6 +294,29 @@ def run_mid(block, x, temb, mode):
     return x
 
 
+# ----------------------------------------------------------------------------------------------------------
+# parallel graph branches (only under CUDA-graph capture: in eager mode the stream bookkeeping is host time)
+# ----------------------------------------------------------------------------------------------------------
+_SIDE = {}
+_FORCE_PAR = [None]      # sampler override: True / False / None (= environment default, CNB_BRANCH_PARALLEL)
+
+
+def capture_parallel():
+    """'0' (no forks), '1' (default: the four-stream ControlNet layout) or '2' (round-1 layout: only the two-encoder
+    fork) while the current stream is capturing; '0' otherwise."""
+    env = _os.environ.get("CNB_BRANCH_PARALLEL", "1")
+    if _FORCE_PAR[0] is not None:
+        env = env if (_FORCE_PAR[0] and env != "0") else ("1" if _FORCE_PAR[0] else "0")
+    return env if (env != "0" and torch.cuda.is_current_stream_capturing()) else "0"
+
+
+def side_stream(dev, which=0):
+    key = (str(dev), torch.cuda.current_stream(dev).cuda_stream, which)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
 def run_up(block, x, skip, temb, mode, cat=None):
     """ConvTranspose (4 parity phases) or identity into the first half of the concat buffer, skip in the second
     half (unet_base.py:267-269).  `cat` may arrive with its second half already written by the producer of the

@@ -174,17 +174,21 @@ def nchw_to_nhwc(x, out=None, out_coff=0):
     return out
 
 
-def nhwc_to_nchw(x, in_coff=0, c=None):
-    """x: (B, H, W, C) channels-last, contiguous or a channel-narrowed view of a wider contiguous buffer."""
+def nhwc_to_nchw(x, in_coff=0, c=None, out=None):
+    """x: (B, H, W, C) channels-last, contiguous or a channel-narrowed view of a wider contiguous buffer.
+    `out`: a contiguous fp32 (B, c, H, W) tensor (e.g. a batch slice of a larger one) to write into."""
     rt.require_cuda(x)
     B, H, W, cv = x.shape
     ld = x.stride(2)
     if x.stride(3) != 1 or x.stride(1) != W * ld or x.stride(0) != H * W * ld or ld < cv:
         raise rt.CnbError("nhwc_to_nchw: expected a channels-last tensor or a channel slice of one")
     c = cv - in_coff if c is None else c
-    if c == 1 and ld == 1 and x.dtype == torch.float32:
-        return x.reshape(B, 1, H, W)
-    out = torch.empty((B, c, H, W), device=x.device, dtype=torch.float32)
+    if out is None:
+        if c == 1 and ld == 1 and x.dtype == torch.float32:
+            return x.reshape(B, 1, H, W)
+        out = torch.empty((B, c, H, W), device=x.device, dtype=torch.float32)
+    elif tuple(out.shape) != (B, c, H, W) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise rt.CnbError("nhwc_to_nchw: out must be a contiguous fp32 (B, c, H, W) tensor")
     rt.check(rt.lib().cnb_nhwc_to_nchw(x.data_ptr(), ld, in_coff, out.data_ptr(), B, c, H * W,
                                        1 if x.dtype == torch.float16 else 0, rt.stream()))
     return out

@@ -40,7 +40,8 @@ if what in ("conv", "all"):
     shapes = [("3x3", 256, 256, 7), ("3x3", 128, 128, 7), ("3x3", 128, 128, 14), ("3x3", 64, 64, 28),
               ("3x3", 64, 128, 14), ("3x3", 32, 64, 28), ("3x3", 16, 16, 28), ("3x3", 64, 16, 28),
               ("1x1", 64, 192, 28), ("1x1", 64, 64, 28), ("1x1", 256, 768, 7), ("1x1", 256, 256, 7),
-              ("4x4s2", 64, 64, 28), ("3x3", 128, 32, 28)]
+              ("4x4s2", 64, 64, 28), ("3x3", 128, 32, 28), ("1x1", 128, 384, 14), ("1x1", 128, 384, 7),
+              ("1x1", 128, 128, 14), ("1x1", 128, 128, 7)]
     only = os.environ.get("CB_ONLY")
     if only:
         shapes = [shapes[int(i)] for i in only.split(",")]
