@@ -660,7 +660,7 @@ def run_b200(args):
                 "config": {"workload": "mnist_ddpm_controlnet_1000step", "batch_per_gpu": B, "global_batch": total,
                            "timesteps_per_sample": STEPS_PER_SAMPLE,
                            "step": "one denoising timestep of this rank's shard: ControlNet eps + fused sample_prev_timestep "
-                                   "(CUDA graph replay; frozen and control encoders as parallel graph branches)",
+                                   "(CUDA graph replay; control encoder, trained encoder + first mid, skip sums and t-embedding rows as parallel graph branches)",
                            "parallelism": f"dp{world}: global batch {total} sharded {B}/rank, no collective in the loop, one "
                                           "all-gather of the final samples (timed in e2e)",
                            "l2": "inputs larger than L2 at %d samples/rank: ~%.1f GB of activations per step vs 126 MB L2" % (
