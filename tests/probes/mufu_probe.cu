@@ -38,6 +38,41 @@ __device__ float run_kind(int kind, int iters, float seed) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a[i]));
     }
+  } else if (kind == 7) {          // cvt.rn.f16x2.f32 (SASS F2FP.F16.F32.PACK_AB): which pipe, what rate?
+    unsigned h[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) h[i] = 0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(a[i]), "f"(a[(i + 1) & 15]));
+        a[i] = __uint_as_float(h[i] | 0x3F000000u);
+      }
+    }
+  } else if (kind == 8) {          // the softmax inner pattern: 2 x (FFMA, MUFU.EX2) + 1 x F2FP per score pair
+    unsigned h[16];
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(0.999f), "f"(-0.001f));
+        asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i + 1]) : "f"(0.999f), "f"(-0.001f));
+        a[i] = ex2f(a[i]);
+        a[i + 1] = ex2f(a[i + 1]);
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(a[i]), "f"(a[i + 1]));
+      }
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) a[i] += __uint_as_float(h[i] & 0x007F0000u);
+    }
+  } else if (kind == 9) {          // the same without the pack (2 x (FFMA, MUFU.EX2))
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(0.999f), "f"(-0.001f));
+        asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i + 1]) : "f"(0.999f), "f"(-0.001f));
+        a[i] = ex2f(a[i]);
+        a[i + 1] = ex2f(a[i + 1]);
+      }
+    }
   } else if (kind == 4) {
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -65,8 +100,10 @@ __global__ void probe(int kindA, int kindB, int iters, long long* out, float* si
 int main() {
   long long* d; float* sink; cudaMalloc(&d, 64); cudaMalloc(&sink, 4096);
   const int iters = 256;   // x16 instructions
-  const char* nm[7] = {"idle", "MUFU", "FFMA-indep", "FFMA-chain", "FFMA+MUFU", "EX2.F16x2", "TANH"};
-  for (int ka : {0, 1, 5}) for (int kb : {0, 1, 5, 6}) {
+  const char* nm[10] = {"idle", "MUFU", "FFMA-indep", "FFMA-chain", "FFMA+MUFU", "EX2.F16x2", "TANH", "F2FP", "softmax8", "softmax8-nopack"};
+  // kinds 8 / 9 issue 8 MUFU per 16-slot iteration: their cyc/instr column is per 1/16 of an iteration (x2 = per MUFU)
+  for (int ka : {0, 1, 5, 7, 8, 9}) for (int kb : {0, 1, 5, 6, 7, 8, 9}) {
+    if (ka > 1 && ka != 7 && kb != 0 && kb != ka) continue;
     probe<<<1, 256>>>(ka, kb, iters, d, sink);
     cudaDeviceSynchronize();
     long long h[8]; cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
