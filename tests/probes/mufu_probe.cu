@@ -1,6 +1,7 @@
 // Does a stream of MUFU.EX2 from one warp starve the other warps of the same SM sub-partition?
 // Block = 8 warps (2 per SMSP: warps w and w+4 share SMSP w%4).  Warps 0..3 run kind A, warps 4..7 run kind B.
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 __device__ __forceinline__ float ex2f(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 // kind: 0 = idle, 1 = independent MUFU x N, 2 = independent FFMA x N, 3 = dependent FFMA chain, 4 = mixed FFMA+MUFU+pack like softmax
@@ -73,6 +74,21 @@ __device__ float run_kind(int kind, int iters, float seed) {
         a[i + 1] = ex2f(a[i + 1]);
       }
     }
+  } else if (kind == 10) {         // mma.sync.m16n8k16 f16 -> f32 (SASS HMMA.16816.F32), four independent accumulators
+    float c[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = a[j];
+    const unsigned fa0 = __float_as_uint(a[4]), fa1 = __float_as_uint(a[5]), fa2 = __float_as_uint(a[6]), fa3 = __float_as_uint(a[7]);
+    const unsigned fb0 = __float_as_uint(a[8]), fb1 = __float_as_uint(a[9]);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                     : "+f"(c[i & 3][0]), "+f"(c[i & 3][1]), "+f"(c[i & 3][2]), "+f"(c[i & 3][3])
+                     : "r"(fa0), "r"(fa1), "r"(fa2), "r"(fa3), "r"(fb0), "r"(fb1));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] = c[j][0] + c[j][1] + c[j][2] + c[j][3];
   } else if (kind == 4) {
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -100,10 +116,11 @@ __global__ void probe(int kindA, int kindB, int iters, long long* out, float* si
 int main() {
   long long* d; float* sink; cudaMalloc(&d, 64); cudaMalloc(&sink, 4096);
   const int iters = 256;   // x16 instructions
-  const char* nm[10] = {"idle", "MUFU", "FFMA-indep", "FFMA-chain", "FFMA+MUFU", "EX2.F16x2", "TANH", "F2FP", "softmax8", "softmax8-nopack"};
+  const char* nm[11] = {"idle", "MUFU", "FFMA-indep", "FFMA-chain", "FFMA+MUFU", "EX2.F16x2", "TANH", "F2FP", "softmax8", "softmax8-nopack", "HMMA.16816"};
   // kinds 8 / 9 issue 8 MUFU per 16-slot iteration: their cyc/instr column is per 1/16 of an iteration (x2 = per MUFU)
-  for (int ka : {0, 1, 5, 7, 8, 9}) for (int kb : {0, 1, 5, 6, 7, 8, 9}) {
-    if (ka > 1 && ka != 7 && kb != 0 && kb != ka) continue;
+  for (int ka : {0, 1, 5, 7, 8, 9, 10}) for (int kb : {0, 1, 5, 6, 7, 8, 9, 10, 2}) {
+    if (ka > 1 && ka != 7 && ka != 10 && kb != 0 && kb != ka) continue;
+    if (const char* only = getenv("PROBE_ONLY_HMMA")) { if (only[0] == '1' && ka != 10 && kb != 10) continue; }
     probe<<<1, 256>>>(ka, kb, iters, d, sink);
     cudaDeviceSynchronize();
     long long h[8]; cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
