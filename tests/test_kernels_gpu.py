@@ -409,6 +409,14 @@ def test_layout_and_scale(pk):
     wide = torch.zeros(3, 6, 7, 16, device="cuda", dtype=torch.float16)
     wide[..., :5] = f16
     assert torch.equal(ops.edm_combine_to_nchw(a.cuda(), x.cuda(), c.cuda(), wide[..., :5]).cpu(), want16)
+    with pytest.raises(rt.CnbError):                      # x must be the fp32 NCHW tensor matching f
+        ops.edm_combine_to_nchw(a.cuda(), x.cuda()[:, :4].contiguous(), c.cuda(), f)
+    # nhwc_to_nchw into a caller-provided batch slice
+    big = torch.full((5, 5, 6, 7), -1.0, device="cuda")
+    ops.nhwc_to_nchw(nhwc(x).cuda(), out=big[1:4])
+    assert torch.equal(big[1:4].cpu(), x) and bool((big[0] == -1).all()) and bool((big[4] == -1).all())
+    with pytest.raises(rt.CnbError):
+        ops.nhwc_to_nchw(nhwc(x).cuda(), out=big[:, :, :, :6])
 
 
 def test_no_cpu_fallback(pk):
