@@ -62,10 +62,11 @@ def controlnet_forward(trained, control, down_zero, mid_zero, hint_feat_fn, x, t
     # i-1; the skip sums need the two encoders but nothing needs them before the decoder.  Under CUDA-graph capture the
     # forward is therefore laid out on four streams (forked / joined with events = parallel graph branches):
     #     cur  : trained conv_in -> downs -> mids[0] -> wait(control mid 0) inject -> mids[1] -> wait(...) inject -> ups
-    #     side : control t-embedding -> conv_in + hint -> downs -> mids[0] -> mids[1]
+    #     side : control conv_in + hint feature -> downs -> mids[0] -> mids[1]
     #     skip : trained t-embedding rows; later wait(both encoders) -> the skip sums
     #     aux  : control t-embedding rows
-    # The critical path loses one mid block per mid level and the skip sums (round 2: B = 128 step 2.43 -> see DESIGN 5);
+    # The critical path loses one mid block per mid level, the skip sums and the t-embedding launches (measured, MNIST:
+    # step at 128 samples 2.42 -> 2.24 ms, at 1024 samples 11.98 -> 11.80 ms; CelebHQ LDM at 256: 28.25 -> 27.7 ms);
     # the kernels of one branch fill the pipes the other leaves idle (MUFU-bound attention next to tensor- / HBM-bound
     # convolutions and GroupNorms).  Same kernels, same inputs, same order per tensor: results are bit-identical to the
     # sequential schedule.  CNB_BRANCH_PARALLEL=0 turns it off; CNB_BRANCH_PARALLEL=2 is the round-1 layout (control
